@@ -1,0 +1,261 @@
+// sgmm_capi.cu -- the C ABI of include/sgmm.h: handles, argument checking, host<->device staging.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include "sgmm_internal.h"
+#include "sgmm_step_core.h"
+
+namespace sgmm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return SGMM_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? SGMM_ERR_NOMEM : SGMM_ERR_CUDA;
+}
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int ensure_workspace(sgmm_bundle* b, size_t bytes)
+{
+    if (b->ws_bytes >= bytes) return SGMM_OK;
+    if (b->ws) { cudaFree(b->ws); b->ws = nullptr; b->ws_bytes = 0; }
+    size_t want = bytes + bytes / 4 + 4096;
+    if (int rc = check_cuda(cudaMalloc(&b->ws, want), "cudaMalloc(workspace)")) return rc;
+    b->ws_bytes = want;
+    return SGMM_OK;
+}
+
+static int fill_pop(const sgmm_population* p, const char* name, PopArgs& out, int64_t G)
+{
+    if (p->count < 0) { set_error("%s.count < 0", name); return SGMM_ERR_INVALID; }
+    if (!p->genomes && !p->master) { set_error("%s: neither genomes nor master given", name); return SGMM_ERR_INVALID; }
+    (void)G;
+    out.genomes = p->genomes; out.master = p->master; out.first_index_dev = nullptr;
+    out.sigma = p->sigma; out.sigma_dev = nullptr; out.seed = p->seed; out.generation = p->generation;
+    out.generation_dev = nullptr; out.first_index = p->first_index; out.count = p->count;
+    return SGMM_OK;
+}
+
+}  // namespace sgmm
+
+using namespace sgmm;
+
+extern "C" {
+
+int sgmm_version(void) { return SGMM_VERSION; }
+const char* sgmm_last_error(void) { return g_err; }
+
+int sgmm_device_count(void)
+{
+    int n = 0;
+    if (int rc = check_cuda(cudaGetDeviceCount(&n), "cudaGetDeviceCount")) return rc;
+    return n;
+}
+
+int sgmm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem)
+{
+    cudaDeviceProp p;
+    if (int rc = check_cuda(cudaGetDeviceProperties(&p, device), "cudaGetDeviceProperties")) return rc;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = (uint64_t)p.totalGlobalMem;
+    return SGMM_OK;
+}
+
+int sgmm_bundle_create(sgmm_bundle** out, int64_t T, const float* z1, const float* z2,
+                       const double* mid_next, const double* best_ask, const double* best_bid,
+                       const double* buy_max, const double* sell_min, double tick_size,
+                       int device, void* stream)
+{
+    if (!out) { set_error("out is NULL"); return SGMM_ERR_INVALID; }
+    *out = nullptr;
+    if (T < 0) { set_error("T < 0"); return SGMM_ERR_INVALID; }
+    if (T > 0 && (!z1 || !z2 || !mid_next || !best_ask || !best_bid || !buy_max || !sell_min)) {
+        set_error("NULL bar array with T > 0"); return SGMM_ERR_INVALID;
+    }
+    if (!(tick_size > 0.0) || !std::isfinite(tick_size)) {
+        set_error("tick_size must be finite and > 0 (fill thresholds rely on the quote being monotone in the offset)");
+        return SGMM_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError())); return SGMM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (int rc = check_cuda(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return rc;
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return SGMM_ERR_UNSUPPORTED; }
+    sgmm_bundle* b = new (std::nothrow) sgmm_bundle();
+    if (!b) { set_error("out of host memory"); return SGMM_ERR_NOMEM; }
+    b->device = device; b->T = T; b->tick = tick_size;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SGMM_OK;
+    float* dz = nullptr; double* dd = nullptr;
+    if (T > 0) {
+        const size_t n = (size_t)T;
+        if (!rc) rc = check_cuda(cudaMalloc(&b->sig, n * sizeof(BarSig)), "cudaMalloc(sig)");
+        if (!rc) rc = check_cuda(cudaMalloc(&b->px, n * sizeof(BarPx)), "cudaMalloc(px)");
+        if (!rc) rc = check_cuda(cudaMalloc(&b->bmax, n * sizeof(double)), "cudaMalloc(buy_max)");
+        if (!rc) rc = check_cuda(cudaMalloc(&b->smin, n * sizeof(double)), "cudaMalloc(sell_min)");
+        if (!rc) rc = check_cuda(cudaMalloc(&dz, 2 * n * sizeof(float)), "cudaMalloc(z staging)");
+        if (!rc) rc = check_cuda(cudaMalloc(&dd, 3 * n * sizeof(double)), "cudaMalloc(price staging)");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(dz, z1, n * sizeof(float), cudaMemcpyHostToDevice, st), "H2D z1");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(dz + n, z2, n * sizeof(float), cudaMemcpyHostToDevice, st), "H2D z2");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(dd, mid_next, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D mid_next");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(dd + n, best_ask, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D best_ask");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(dd + 2 * n, best_bid, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D best_bid");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(b->bmax, buy_max, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D buy_max");
+        if (!rc) rc = check_cuda(cudaMemcpyAsync(b->smin, sell_min, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D sell_min");
+        if (!rc) rc = launch_prologue(b, dz, dz + n, dd, dd + n, dd + 2 * n, st);
+        if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "bundle prologue");
+        cudaFree(dz); cudaFree(dd);
+    }
+    if (rc) { sgmm_bundle_destroy(b); return rc; }
+    *out = b;
+    return SGMM_OK;
+}
+
+int sgmm_bundle_length(const sgmm_bundle* b, int64_t* T)
+{
+    if (!b || !T) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
+    *T = b->T; return SGMM_OK;
+}
+
+int sgmm_bundle_device(const sgmm_bundle* b, int* device)
+{
+    if (!b || !device) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
+    *device = b->device; return SGMM_OK;
+}
+
+int sgmm_bundle_thresholds(const sgmm_bundle* b, int32_t* ka, int32_t* kb, void* stream)
+{
+    if (!b) { set_error("bundle is NULL"); return SGMM_ERR_INVALID; }
+    if (b->T == 0) return SGMM_OK;
+    DeviceGuard guard(b->device);
+    BarSig* h = (BarSig*)malloc((size_t)b->T * sizeof(BarSig));
+    if (!h) { set_error("out of host memory"); return SGMM_ERR_NOMEM; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemcpyAsync(h, b->sig, (size_t)b->T * sizeof(BarSig), cudaMemcpyDeviceToHost, st), "D2H thresholds");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "D2H thresholds");
+    if (!rc) for (int64_t t = 0; t < b->T; ++t) {
+        // stored as threshold+1 (strict compare); report the threshold itself, sentinels unchanged
+        if (ka) ka[t] = (h[t].ka1 == K_NEVER || h[t].ka1 == K_ALWAYS) ? h[t].ka1 : h[t].ka1 - 1;
+        if (kb) kb[t] = (h[t].kb1 == K_NEVER || h[t].kb1 == K_ALWAYS) ? h[t].kb1 : h[t].kb1 - 1;
+    }
+    free(h);
+    return rc;
+}
+
+int sgmm_bundle_destroy(sgmm_bundle* b)
+{
+    if (!b) return SGMM_OK;
+    {
+        DeviceGuard guard(b->device);
+        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->ws);
+    }
+    delete b;
+    return SGMM_OK;
+}
+
+static int check_rollout_args(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                              const sgmm_rollout_params* params, const double* fitness, const int32_t* trades)
+{
+    if (!bundle || !mm || !params) { set_error("NULL bundle / mm / params"); return SGMM_ERR_INVALID; }
+    if (mm->count > 0 && (!fitness || !trades)) { set_error("NULL output array"); return SGMM_ERR_INVALID; }
+    if (params->precision != SGMM_PRECISION_F32) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
+    if (adv && adv->count != mm->count) { set_error("adv.count (%lld) != mm.count (%lld): MM i meets adversary i (Env/drl_engine.py:115)", (long long)adv->count, (long long)mm->count); return SGMM_ERR_INVALID; }
+    if (adv && adv->hidden != 32) { set_error("adversary genomes are 1250-float TradingPolicy(32) genomes (models/model.py:63)"); return SGMM_ERR_INVALID; }
+    return SGMM_OK;
+}
+
+int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                            const sgmm_rollout_params* params, double* fitness, int32_t* trades, void* stream)
+{
+    if (int rc = check_rollout_args(bundle, mm, adv, params, fitness, trades)) return rc;
+    PopArgs pm, pa;
+    if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
+    if (adv) if (int rc = fill_pop(adv, "adv", pa, 1250)) return rc;
+    DeviceGuard guard(bundle->device);
+    return launch_rollout(bundle, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
+                          params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
+}
+
+int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                                 const sgmm_rollout_params* params, double* fitness, int32_t* trades, void* stream)
+{
+    if (int rc = check_rollout_args(bundle, mm, adv, params, fitness, trades)) return rc;
+    if (mm->count == 0) return SGMM_OK;
+    sgmm_bundle* b = const_cast<sgmm_bundle*>(bundle);
+    std::lock_guard<std::mutex> lock(b->ws_mutex);
+    DeviceGuard guard(b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t P = mm->count, G = genome_len(mm->hidden), GA = 1250;
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t mm_bytes = align((size_t)(mm->genomes ? P * G : G) * sizeof(float));
+    const size_t adv_bytes = adv ? align((size_t)(adv->genomes ? P * GA : GA) * sizeof(float)) : 0;
+    const size_t fit_bytes = align((size_t)P * sizeof(double)), trd_bytes = align((size_t)P * sizeof(int32_t));
+    if (int rc = ensure_workspace(b, mm_bytes + adv_bytes + fit_bytes + trd_bytes)) return rc;
+    char* base = (char*)b->ws;
+    float* d_mm = (float*)base; float* d_adv = (float*)(base + mm_bytes);
+    double* d_fit = (double*)(base + mm_bytes + adv_bytes); int32_t* d_trd = (int32_t*)(base + mm_bytes + adv_bytes + fit_bytes);
+    PopArgs pm, pa;
+    if (int rc = fill_pop(mm, "mm", pm, G)) return rc;
+    const float* hsrc = mm->genomes ? mm->genomes : mm->master;
+    if (int rc = check_cuda(cudaMemcpyAsync(d_mm, hsrc, (size_t)(mm->genomes ? P * G : G) * sizeof(float), cudaMemcpyHostToDevice, st), "H2D genomes")) return rc;
+    if (mm->genomes) pm.genomes = d_mm; else pm.master = d_mm;
+    if (adv) {
+        if (int rc = fill_pop(adv, "adv", pa, GA)) return rc;
+        const float* asrc = adv->genomes ? adv->genomes : adv->master;
+        if (int rc = check_cuda(cudaMemcpyAsync(d_adv, asrc, (size_t)(adv->genomes ? P * GA : GA) * sizeof(float), cudaMemcpyHostToDevice, st), "H2D adversary genomes")) return rc;
+        if (adv->genomes) pa.genomes = d_adv; else pa.master = d_adv;
+    }
+    if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
+                                params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
+    if (int rc = check_cuda(cudaMemcpyAsync(fitness, d_fit, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H fitness")) return rc;
+    if (int rc = check_cuda(cudaMemcpyAsync(trades, d_trd, (size_t)P * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "D2H trades")) return rc;
+    return check_cuda(cudaStreamSynchronize(st), "rollout_population_host");
+}
+
+int sgmm_rollout_trace(const sgmm_bundle* bundle, const float* mm_genome, int32_t hidden, const float* adv_genome,
+                       const int32_t* forced_actions, const sgmm_rollout_params* params, const sgmm_trace* trace,
+                       double* fitness, int32_t* trades, void* stream)
+{
+    if (!bundle || !params) { set_error("NULL bundle / params"); return SGMM_ERR_INVALID; }
+    DeviceGuard guard(bundle->device);
+    return launch_trace(bundle, mm_genome, hidden, adv_genome, forced_actions, params->phi, params->fee_rate,
+                        trace, fitness, trades, (cudaStream_t)stream);
+}
+
+int sgmm_env_init(sgmm_env_state* e, double phi, double tick_size, double fee_rate)
+{
+    if (!e) { set_error("env is NULL"); return SGMM_ERR_INVALID; }
+    e->fee_rate = fee_rate; e->phi = phi; e->tick_size = tick_size;     // market_env.py:9-11
+    e->inventory = 0; e->cash = 0.0; e->i_max = 2; e->i_min = -2;       // :12-15
+    return SGMM_OK;
+}
+
+int sgmm_env_step_host(sgmm_env_state* e, const int64_t action[2], const int64_t* adv_action, double mid_next,
+                       double best_ask, double best_bid, double buy_max, double sell_min, sgmm_step_info* info)
+{
+    if (!e || !action || !info) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
+    int64_t off_a = action[0], off_b = action[1];                        // market_env.py:23
+    if (adv_action) { off_a += adv_action[0]; off_b += adv_action[1]; }  // :25-28
+    env_step(*e, off_a, off_b, mid_next, best_ask, best_bid, buy_max, sell_min, *info);
+    return SGMM_OK;
+}
+
+}  // extern "C"

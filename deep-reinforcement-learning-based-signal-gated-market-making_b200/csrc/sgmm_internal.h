@@ -1,0 +1,79 @@
+// sgmm_internal.h -- shared declarations between the translation units of libsgmm_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+#include "../../include/sgmm.h"
+
+namespace sgmm {
+
+// One bar as the kernels see it.  16 B signal/threshold record + 32 B price record.
+struct __align__(16) BarSig {
+    float z1, z2;        // normalised SGU1 / SGU2 signals (drl_engine.py:33-34), fp32
+    int32_t ka1, kb1;    // fill thresholds + 1: fill_sell <=> off_a < ka1, fill_buy <=> off_b < kb1
+};                       // INT32_MIN = never, INT32_MAX = always
+struct __align__(32) BarPx {
+    double ask, bid, mid_next, pad;
+};
+
+constexpr int32_t K_NEVER = INT32_MIN;
+constexpr int32_t K_ALWAYS = INT32_MAX;
+constexpr int32_t K_CLAMP = 1 << 30;
+
+}  // namespace sgmm
+
+struct sgmm_bundle {
+    int device = 0;
+    int64_t T = 0;
+    double tick = 0.0;
+    sgmm::BarSig* sig = nullptr;       // [T]
+    sgmm::BarPx* px = nullptr;         // [T]
+    double* bmax = nullptr;            // [T] raw bounds (trace kernel runs the literal step core)
+    double* smin = nullptr;
+    // grow-only workspace of the *_host entry points
+    std::mutex ws_mutex;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+namespace sgmm {
+
+// device-side population descriptor
+struct PopArgs {
+    const float* genomes;   // [count,G] or nullptr
+    const float* master;    // [G]
+    const int64_t* first_index_dev;   // optional device scalar added to first_index (GA: best child)
+    float sigma;
+    const float* sigma_dev;           // optional device scalar overriding sigma (GA sigma decay)
+    uint64_t seed;
+    uint64_t generation;
+    const int32_t* generation_dev;    // optional device scalar overriding generation
+    int64_t first_index;
+    int64_t count;
+};
+
+struct RolloutArgs {
+    const BarSig* sig;
+    const BarPx* px;
+    int64_t T;
+    double tick, phi, fee;
+    PopArgs mm, adv;
+    double* fitness;
+    int32_t* trades;
+};
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, int hidden,
+                   double phi, double fee, int units_per_lane, int warps_per_cta,
+                   double* fitness, int32_t* trades, cudaStream_t st);
+int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const float* adv_genome,
+                 const int32_t* forced, double phi, double fee, const sgmm_trace* tr,
+                 double* fitness, int32_t* trades, cudaStream_t st);
+int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,
+                    const double* ask, const double* bid, cudaStream_t st);
+
+inline int64_t genome_len(int H) { return (int64_t)H * H + 7 * (int64_t)H + 2; }
+
+}  // namespace sgmm

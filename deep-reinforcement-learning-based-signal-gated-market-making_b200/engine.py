@@ -1,0 +1,339 @@
+"""Population rollout, per-individual evaluation and the GA engine on the B200.
+
+Reference surface kept verbatim (Env/drl_engine.py):
+  ``evaluate_individual(mm_weights, adv_weights, bundle, phi, tick_size, fee_rate, train_stats,
+  use_arl=False) -> (total_reward, trades)``                                           (:9-67)
+  ``DRLEngine(pop_size, sigma, phi, tick_size, fee_rate, use_arl, save_dir)``, ``.mm_evolver``,
+  ``.adv_evolver``, ``.train(train_bundle, val_bundle, train_stats, generations, output_prefix)
+  -> (master_policy, history)``                                                        (:69-178)
+plus the population-level calls the reference spells ``Pool.starmap`` (:104-115).
+Everything computes through the C ABI of libsgmm_b200.so; nothing here touches ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bundle import Bundle
+from .policy import NeuroEvolution, TradingPolicy, genome_len
+
+ADV_SEED_FLIP = 0x8000000000000000       # adversary noise stream = seed with the top bit flipped
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _params(phi, fee_rate, units_per_lane=0, warps_per_cta=0):
+    return _lib.RolloutParams(float(phi), float(fee_rate), 0, 0, int(units_per_lane), int(warps_per_cta))
+
+
+def _as_f32_matrix(x, width):
+    """Accept a list of 1-D tensors (NeuroEvolution.ask), a 2-D tensor or ndarray."""
+    if isinstance(x, (list, tuple)):
+        x = torch.stack([torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in x])
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    x = x.to(torch.float32)
+    if x.dim() == 1:
+        x = x.reshape(1, -1)
+    if x.shape[1] != width:
+        raise ValueError(f"genome length {x.shape[1]} != {width}")
+    return x.contiguous()
+
+
+def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_rate=0.0, hidden=32,
+                       units_per_lane=0, warps_per_cta=0):
+    """One episode per individual (the reference's ``pool.starmap(evaluate_individual, ...)``).
+
+    ``genomes``: [P, G] float32 -- CUDA tensor (device path, returns CUDA tensors, no sync) or
+    CPU tensor / ndarray / list of tensors (end-to-end path through ``sgmm_rollout_population_host``:
+    H2D, kernel, D2H, returns numpy arrays).  ``adv_genomes``: optional [P, 1250] (use_arl).
+    Returns ``(fitness float64[P], trades int32[P])``.
+    """
+    G = genome_len(hidden)
+    g = _as_f32_matrix(genomes, G)
+    P = g.shape[0]
+    a = None if adv_genomes is None else _as_f32_matrix(adv_genomes, 1250)
+    if a is not None and a.shape[0] != P:
+        raise ValueError("adversary population size differs from the market-maker population")
+    L = _lib.lib()
+    mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    adv = None if a is None else _lib.Population(32, 0, P, a.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta)
+    advp = None if adv is None else C.byref(adv)
+    if g.is_cuda:
+        if g.device.index != bundle.device or (a is not None and a.device != g.device):
+            raise ValueError("genomes must live on the bundle's device")
+        fit = torch.empty(P, dtype=torch.float64, device=g.device)
+        trd = torch.empty(P, dtype=torch.int32, device=g.device)
+        _lib.check(L.sgmm_rollout_population(bundle.handle, C.byref(mm), advp, C.byref(prm),
+                                             fit.data_ptr(), trd.data_ptr(), _stream(bundle.device)))
+        return fit, trd
+    if a is not None and a.is_cuda:
+        raise ValueError("mixing CPU market-maker genomes with CUDA adversary genomes")
+    fit = np.empty(P, np.float64)
+    trd = np.empty(P, np.int32)
+    _lib.check(L.sgmm_rollout_population_host(bundle.handle, C.byref(mm), advp, C.byref(prm),
+                                              fit.ctypes.data, trd.ctypes.data, _stream(bundle.device)))
+    return fit, trd
+
+
+def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, first_index=0,
+                   adv_master=None, adv_sigma=None, phi, fee_rate=0.0, hidden=32,
+                   units_per_lane=0, warps_per_cta=0):
+    """Evaluate children ``first_index .. first_index+count-1`` of ``master`` without ever storing
+    them: child i = master + sigma*N(0,1)[Philox(seed, generation, i)] is generated inside the
+    kernel (device-resident ``ask``, models/model.py:65-71).  ``master`` (and ``adv_master``) are
+    CUDA float32 tensors; returns CUDA tensors."""
+    G = genome_len(hidden)
+    m = torch.as_tensor(master, dtype=torch.float32, device=f"cuda:{bundle.device}").contiguous()
+    if m.numel() != G:
+        raise ValueError(f"master length {m.numel()} != {G}")
+    fit = torch.empty(count, dtype=torch.float64, device=m.device)
+    trd = torch.empty(count, dtype=torch.int32, device=m.device)
+    mm = _lib.Population(hidden, 0, count, None, m.data_ptr(), float(sigma), 0.0, int(seed), int(generation),
+                         int(first_index))
+    advp = None
+    if adv_master is not None:
+        am = torch.as_tensor(adv_master, dtype=torch.float32, device=m.device).contiguous()
+        if am.numel() != 1250:
+            raise ValueError("adversary master must have 1250 floats (models/model.py:63)")
+        adv = _lib.Population(32, 0, count, None, am.data_ptr(), float(sigma if adv_sigma is None else adv_sigma),
+                              0.0, int(seed) ^ ADV_SEED_FLIP, int(generation), int(first_index))
+        advp = C.byref(adv)
+    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta)
+    _lib.check(_lib.lib().sgmm_rollout_population(bundle.handle, C.byref(mm), advp, C.byref(prm),
+                                                  fit.data_ptr(), trd.data_ptr(), _stream(bundle.device)))
+    return fit, trd
+
+
+_TRACE_I32 = ("off_a", "off_b", "adv_a", "adv_b", "fill_buy", "fill_sell", "inventory")
+_TRACE_F64 = ("cash", "reward", "pnl_reward", "inventory_reward", "fee_paid")
+_TRACE_F32 = ("raw_a", "raw_b")
+
+
+def rollout_trace(bundle: Bundle, genome=None, adv_genome=None, forced_actions=None, *, phi,
+                  fee_rate=0.0, hidden=32):
+    """Per-step trace of one individual: the recorder row contract (Env/recorder.py:8-36,
+    main.py:74-90).  ``forced_actions`` int32[T,2] replaces the policy (teacher-forced replay).
+    Returns ``(fitness, trades, dict of numpy arrays of length T)``."""
+    dev = torch.device(f"cuda:{bundle.device}")
+    T = bundle.T
+    cols = {k: torch.zeros(T, dtype=torch.int32, device=dev) for k in _TRACE_I32}
+    cols.update({k: torch.zeros(T, dtype=torch.float64, device=dev) for k in _TRACE_F64})
+    cols.update({k: torch.zeros(T, dtype=torch.float32, device=dev) for k in _TRACE_F32})
+    tr = _lib.Trace(*[cols[n].data_ptr() for n, _ in _lib.Trace._fields_])
+    g = None if genome is None else torch.as_tensor(genome, dtype=torch.float32).reshape(-1).to(dev).contiguous()
+    a = None if adv_genome is None else torch.as_tensor(adv_genome, dtype=torch.float32).reshape(-1).to(dev).contiguous()
+    f = None
+    if forced_actions is not None:
+        f = torch.as_tensor(np.ascontiguousarray(forced_actions, np.int32)).reshape(-1).to(dev).contiguous()
+        if f.numel() != 2 * T:
+            raise ValueError("forced_actions must be [T, 2]")
+    if g is not None and g.numel() != genome_len(hidden):
+        raise ValueError("bad genome length")
+    fit = torch.zeros(1, dtype=torch.float64, device=dev)
+    trd = torch.zeros(1, dtype=torch.int32, device=dev)
+    prm = _params(phi, fee_rate)
+    _lib.check(_lib.lib().sgmm_rollout_trace(
+        bundle.handle, None if g is None else g.data_ptr(), hidden, None if a is None else a.data_ptr(),
+        None if f is None else f.data_ptr(), C.byref(prm), C.byref(tr), fit.data_ptr(), trd.data_ptr(),
+        _stream(bundle.device)))
+    out = {k: v.cpu().numpy() for k, v in cols.items()}
+    return float(fit.item()), int(trd.item()), out
+
+
+def measure_fp32_peak(device=0) -> float:
+    """Sustained FP32 FMA TFLOP/s of the device (roofline denominator for H=32)."""
+    v = C.c_double()
+    _lib.check(_lib.lib().sgmm_measure_fp32_peak(int(device), C.byref(v), _stream(device)))
+    return v.value
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluate_individual: reference signature, one individual per call
+# ------------------------------------------------------------------------------------------------
+_BUNDLE_CACHE: "OrderedDict[tuple, Bundle]" = OrderedDict()
+_BUNDLE_CACHE_MAX = 8
+
+
+def _cached_bundle(bundle, train_stats, tick_size, device=None) -> Bundle:
+    """Upload a host 7-tuple once; later calls with the same arrays reuse the device copy (the
+    reference re-pickles the bundle to its workers every generation, drl_engine.py:104-115)."""
+    if isinstance(bundle, Bundle):
+        return bundle
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = (tuple(id(a) for a in bundle), tuple(len(a) for a in bundle), float(tick_size), dev,
+           tuple((k, float(train_stats[k]), np.asarray(train_stats[k]).dtype.str)
+                 for k in ("s1_m", "s1_s", "s2_m", "s2_s")))
+    b = _BUNDLE_CACHE.get(key)
+    if b is None:
+        b = Bundle.from_arrays(bundle, train_stats, tick_size, dev)
+        b._keepalive = bundle          # ids stay unique while cached
+        _BUNDLE_CACHE[key] = b
+        while len(_BUNDLE_CACHE) > _BUNDLE_CACHE_MAX:
+            _BUNDLE_CACHE.popitem(last=False)[1].close()
+    else:
+        _BUNDLE_CACHE.move_to_end(key)
+    return b
+
+
+def evaluate_individual(mm_weights, adv_weights, bundle, phi, tick_size, fee_rate, train_stats,
+                        use_arl=False):
+    """Drop-in for Env/drl_engine.py:9-67 -> ``(np.float64 total_reward, int trades)``."""
+    dev_bundle = _cached_bundle(bundle, train_stats, tick_size)
+    adv = adv_weights if (use_arl and adv_weights is not None) else None      # :17-21
+    mm = torch.as_tensor(mm_weights, dtype=torch.float32).reshape(1, -1).cpu()
+    if adv is not None:
+        adv = torch.as_tensor(adv, dtype=torch.float32).reshape(1, -1).cpu()
+    fit, trd = rollout_population(dev_bundle, mm, adv, phi=phi, fee_rate=fee_rate)
+    return np.float64(fit[0]), int(trd[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# DRLEngine
+# ------------------------------------------------------------------------------------------------
+class DeviceGA:
+    """Thin owner of a ``sgmm_ga`` handle (include/sgmm.h): ask/evaluate/tell/validate/select on
+    the device, one call per generation, no host round trip."""
+
+    def __init__(self, mm_master, adv_master=None, *, pop_size, sigma, phi, fee_rate, use_arl, seed,
+                 max_generations, patience=15, hidden=32, device=None, shard=None):
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        first, count = (0, pop_size) if shard is None else shard
+        cfg = _lib.GaConfig(hidden, int(bool(use_arl)), pop_size, first, count, float(sigma), patience,
+                            float(phi), float(fee_rate), int(seed), int(max_generations), 0)
+        m = np.ascontiguousarray(torch.as_tensor(mm_master).detach().cpu().numpy(), np.float32)
+        a = None
+        if use_arl:
+            a = np.ascontiguousarray(torch.as_tensor(adv_master).detach().cpu().numpy(), np.float32)
+        self.G = genome_len(hidden)
+        self.pop_size, self.shard, self.max_generations = pop_size, (first, count), max_generations
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().sgmm_ga_create(C.byref(self._h), C.byref(cfg), m.ctypes.data,
+                                             None if a is None else a.ctypes.data, self.device,
+                                             _stream(self.device)))
+
+    def buffers(self):
+        """(fitness_slice, trades_slice, fitness_all, trades_all) raw device addresses."""
+        p = [C.c_void_p() for _ in range(4)]
+        _lib.check(_lib.lib().sgmm_ga_buffers(self._h, *[C.byref(x) for x in p]))
+        return tuple(x.value for x in p)
+
+    def evaluate(self, train: Bundle):
+        _lib.check(_lib.lib().sgmm_ga_evaluate(self._h, train.handle, _stream(self.device)))
+
+    def select(self, val: Bundle):
+        _lib.check(_lib.lib().sgmm_ga_select(self._h, val.handle, _stream(self.device)))
+
+    def generation(self, train: Bundle, val: Bundle):
+        _lib.check(_lib.lib().sgmm_ga_generation(self._h, train.handle, val.handle, _stream(self.device)))
+
+    def status(self):
+        s = _lib.GaStatus()
+        _lib.check(_lib.lib().sgmm_ga_status_host(self._h, C.byref(s), _stream(self.device)))
+        return {"generation": s.generation, "stale": s.stale, "sigma": s.sigma, "adv_sigma": s.adv_sigma,
+                "best_val": s.best_val, "last_best_index": s.last_best_index}
+
+    def masters(self):
+        mm = np.empty(self.G, np.float32)
+        adv = np.empty(1250, np.float32)
+        best = np.empty(self.G, np.float32)
+        _lib.check(_lib.lib().sgmm_ga_master_host(self._h, mm.ctypes.data, adv.ctypes.data, best.ctypes.data,
+                                                  _stream(self.device)))
+        return mm, adv, best
+
+    def history(self, n=None):
+        n = self.max_generations if n is None else int(n)
+        tf, vf = np.empty(n, np.float64), np.empty(n, np.float64)
+        tt, vt = np.empty(n, np.int32), np.empty(n, np.int32)
+        sg = np.empty(n, np.float32)
+        _lib.check(_lib.lib().sgmm_ga_history_host(self._h, n, tf.ctypes.data, vf.ctypes.data, tt.ctypes.data,
+                                                   vt.ctypes.data, sg.ctypes.data, _stream(self.device)))
+        return {"train_f": tf, "val_f": vf, "train_trades": tt, "val_trades": vt, "sigma": sg}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().sgmm_ga_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DRLEngine:
+    """Drop-in for Env/drl_engine.py:69-178.  Same constructor, attributes and return values; the
+    generation loop runs on the device (:class:`DeviceGA`).  Extra keyword arguments (``seed``,
+    ``device``, ``patience``) expose what the reference hard-codes or leaves to the global RNG."""
+
+    def __init__(self, pop_size=50, sigma=0.05, phi=0.01, tick_size=0.01, fee_rate=0.0, use_arl=False,
+                 save_dir="checkpoints/drl", seed=0, device=None, patience=15):
+        self.phi = phi
+        self.tick_size = tick_size
+        self.fee_rate = fee_rate
+        self.save_dir = save_dir
+        os.makedirs(self.save_dir, exist_ok=True)
+        self.use_arl = use_arl
+        self.seed = seed
+        self.device = device
+        self.patience = patience
+        self.mm_evolver = NeuroEvolution(population_size=pop_size, sigma=sigma)
+        if self.use_arl:
+            self.adv_evolver = NeuroEvolution(population_size=pop_size, sigma=sigma)
+
+    def train(self, train_bundle, val_bundle, train_stats, generations=100, output_prefix="agent",
+              log_every=5, verbose=True):
+        dev = torch.cuda.current_device() if self.device is None else int(self.device)
+        train = _cached_bundle(train_bundle, train_stats, self.tick_size, dev)
+        val = _cached_bundle(val_bundle, train_stats, self.tick_size, dev)
+        history = {'gen': [], 'train_f': [], 'val_f': [], 'train_trades': [], 'val_trades': []}
+        save_path = os.path.join(self.save_dir, f"{output_prefix}_best_val_{self.phi}.pth")
+        ga = DeviceGA(self.mm_evolver.master_policy.get_weights(),
+                      self.adv_evolver.master_policy.get_weights() if self.use_arl else None,
+                      pop_size=self.mm_evolver.pop_size, sigma=self.mm_evolver.sigma, phi=self.phi,
+                      fee_rate=self.fee_rate, use_arl=self.use_arl, seed=self.seed,
+                      max_generations=max(1, generations), patience=self.patience, device=dev)
+        try:
+            logged = 0
+            for gen in range(generations):
+                ga.generation(train, val)                       # ask + evaluate + tell + validate + select
+                if verbose and gen % log_every == 0:            # drl_engine.py:169-171
+                    h = ga.history(gen + 1)
+                    best_so_far = np.maximum.accumulate(h["val_f"])
+                    for g in range(logged, gen + 1):
+                        if g > 0 and h["sigma"][g] != h["sigma"][g - 1]:
+                            print(f">>> Sigma decayed to {h['sigma'][g]:.4f} due to no improvement")
+                    logged = gen + 1
+                    tag = "*" if (gen == 0 or h["val_f"][gen] > best_so_far[gen - 1]) else ""
+                    arl = "ARL:ON" if self.use_arl else "ARL:OFF"
+                    print(f"Gen {gen:03d} | {arl} | Best Train: {h['train_f'][gen]:.2f} | Val: {h['val_f'][gen]:.2f}{tag}")
+            h = ga.history(generations)
+            st = ga.status()
+            mm, adv, best = ga.masters()
+        finally:
+            ga.close()
+        history['gen'] = list(range(generations))
+        history['train_f'] = [np.float64(x) for x in h["train_f"]]
+        history['val_f'] = [np.float64(x) for x in h["val_f"]]
+        history['train_trades'] = [int(x) for x in h["train_trades"]]
+        history['val_trades'] = [int(x) for x in h["val_trades"]]
+        self.mm_evolver.sigma = float(st["sigma"])
+        if self.use_arl:
+            self.adv_evolver.sigma = float(st["adv_sigma"])
+            self.adv_evolver.master_policy.set_weights(torch.from_numpy(adv))
+        # drl_engine.py:144-150,174-176: the checkpoint holds the master of the best validation
+        # generation and is loaded back into the returned policy
+        improved = generations > 0 and st["best_val"] > -np.inf
+        self.mm_evolver.master_policy.set_weights(torch.from_numpy(best if improved else mm))
+        if improved:
+            torch.save(self.mm_evolver.master_policy.state_dict(), save_path)
+        return self.mm_evolver.master_policy, history

@@ -1,0 +1,234 @@
+/*
+ * sgmm.h -- C ABI of the B200-native population rollout for signal-gated market making.
+ *
+ * The reference (KAS-W/Deep-Reinforcement-Learning-Based-Signal-Gated-Market-Making) has no FFI:
+ * its boundary is a plain Python API.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root).  The Python package binds these with ctypes
+ * (see INTEGRATION.md); no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns SGMM_OK (0) or a negative SGMM_ERR_* code and never throws;
+ *     sgmm_last_error() returns a thread-local human-readable message for the last failure.
+ *   - "stream" is a cudaStream_t passed as void* (0 = legacy default stream).  Work is enqueued
+ *     on it; functions taking DEVICE pointers never synchronise.  Functions taking HOST pointers
+ *     (suffix _host, sgmm_bundle_create) copy through internal pinned staging buffers and
+ *     synchronise the stream before returning.
+ *   - the caller owns every buffer it passes in; the library owns only the opaque handles it
+ *     creates (sgmm_*_create / sgmm_*_destroy).
+ *   - genome layout = torch parameters() order of TradingPolicy(hidden=H) (models/model.py:28-36):
+ *       W1[H,3] | b1[H] | W2[H,H] | b2[H] | W3[2,H] | b3[2]          G = H*H + 7H + 2 floats
+ *     AdversaryPolicy (models/model.py:52-57) consumes the first 74 floats of a 1250-float genome:
+ *       V1[12,3] | c1[12] | V2[2,12] | c2[2]
+ *   - offsets: off_a widens the ask (ask + off_a*tick), off_b widens the bid (bid - off_b*tick)
+ *     (Env/market_env.py:23,30-31).  Offsets are carried as int32 and clamped to +-2^30 ticks.
+ */
+#ifndef SGMM_H
+#define SGMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGMM_VERSION 100            /* 0.1.0 */
+
+#define SGMM_OK               0
+#define SGMM_ERR_INVALID     -1     /* bad argument (NULL, negative size, unsupported hidden width) */
+#define SGMM_ERR_CUDA        -2     /* CUDA runtime failure; message carries cudaGetErrorString      */
+#define SGMM_ERR_NOMEM       -3
+#define SGMM_ERR_UNSUPPORTED -4     /* device is not sm_100 class / feature not built                */
+
+/* precision of the policy MLP */
+#define SGMM_PRECISION_F32   0      /* SGMM-F32 order on CUDA cores: bit-identical to the oracle     */
+
+/* rollout flags */
+#define SGMM_FLAG_NONE       0
+
+int sgmm_version(void);
+const char* sgmm_last_error(void);
+/* number of visible CUDA devices, or a negative error */
+int sgmm_device_count(void);
+int sgmm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bundle: the device-resident bar set of one episode.
+ * Replaces the 7-tuple returned by load_signals_bundle (pipeline/agent_trainer.py:75-77) as
+ * consumed by evaluate_individual (Env/drl_engine.py:11).  z1/z2 are the NORMALISED signals
+ * (Env/drl_engine.py:33-34) computed by the caller with its own numpy expression and cast to
+ * float32; the other five arrays are float64, NaN allowed in buy_max / sell_min.
+ * All pointers are HOST pointers of length T (T may be 0).  Besides uploading, creation runs the
+ * prologue kernel that derives the integer fill thresholds
+ *     Ka[t] = max{k : fl(ask + fl(k*tick)) <= buy_max}   Kb[t] = max{k : fl(bid - fl(k*tick)) >= sell_min}
+ * with the reference's exact two-rounding fp64 expression (Env/market_env.py:30-31,37-38).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sgmm_bundle sgmm_bundle;
+
+int sgmm_bundle_create(sgmm_bundle** out, int64_t T,
+                       const float* z1, const float* z2, const double* mid_next,
+                       const double* best_ask, const double* best_bid,
+                       const double* buy_max, const double* sell_min,
+                       double tick_size, int device, void* stream);
+int sgmm_bundle_length(const sgmm_bundle* b, int64_t* T);
+int sgmm_bundle_device(const sgmm_bundle* b, int* device);
+/* copy the derived thresholds back (HOST int32[T] each, either may be NULL); INT32_MIN = never
+ * fills, INT32_MAX = always fills */
+int sgmm_bundle_thresholds(const sgmm_bundle* b, int32_t* ka, int32_t* kb, void* stream);
+int sgmm_bundle_destroy(sgmm_bundle* b);
+
+/* ---------------------------------------------------------------------------------------------
+ * Population: who is evaluated.  Either explicit genomes [count, G] (the list returned by
+ * NeuroEvolution.ask, models/model.py:65-71) or "children of a master": child i is
+ *     master + sigma * N(0,1)[Philox4x32-10 key=seed, counter=(e/4, index_lo, index_hi, generation)]
+ * generated inside the rollout kernel, index = first_index + i (so a sharded population draws
+ * the same children whatever the number of ranks).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t hidden;          /* H; 32 for the reference policy (models/model.py:7)               */
+    int32_t reserved;
+    int64_t count;           /* P                                                                */
+    const float* genomes;    /* [count, G] row-major, or NULL for seeded children                */
+    const float* master;     /* [G], used when genomes == NULL                                   */
+    float sigma;             /* mutation scale (models/model.py:61)                              */
+    float reserved2;
+    uint64_t seed;
+    uint64_t generation;
+    int64_t first_index;
+} sgmm_population;
+
+typedef struct {
+    double phi;              /* inventory penalty (Env/market_env.py:10,57)                      */
+    double fee_rate;         /* proportional fee  (Env/market_env.py:9,46,52)                    */
+    int32_t precision;       /* SGMM_PRECISION_*                                                 */
+    int32_t flags;           /* SGMM_FLAG_*                                                      */
+    int32_t units_per_lane;  /* 0 = auto; 1, 2 or 4 hidden units per lane (tuning knob)          */
+    int32_t warps_per_cta;   /* 0 = auto                                                         */
+} sgmm_rollout_params;
+
+/* Replaces Pool.starmap(evaluate_individual, zip(mm_pop, adv_pop)) (Env/drl_engine.py:104-115):
+ * one full episode per individual, fitness[i] = total_reward (with the -50 no-trade penalty,
+ * Env/drl_engine.py:64-65), trades[i] = number of steps with at least one fill (:60-61).
+ * adv == NULL <=> use_arl False.  adv->count must equal mm->count (MM i meets adversary i).
+ * All pointers inside mm / adv and fitness / trades are DEVICE pointers on the bundle's device. */
+int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm,
+                            const sgmm_population* adv, const sgmm_rollout_params* params,
+                            double* fitness, int32_t* trades, void* stream);
+
+/* Same call with HOST pointers everywhere (genomes / master in, fitness / trades out): uploads,
+ * runs, downloads and synchronises.  This is the end-to-end entry the Python
+ * evaluate_individual / DRLEngine shims use when handed CPU tensors. */
+int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_population* mm,
+                                 const sgmm_population* adv, const sgmm_rollout_params* params,
+                                 double* fitness, int32_t* trades, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-step trace of ONE individual: the recorder row contract (Env/recorder.py:8-36,
+ * main.py:74-90).  Every pointer is a DEVICE array of length T and may be NULL.
+ * forced_actions (DEVICE int32[T,2], may be NULL) replaces the policy: teacher-forced replay of
+ * recorded actions through the step core (bit-exact integer work given identical actions).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t* off_a; int32_t* off_b;      /* MM action (before the adversary's displacement)      */
+    int32_t* adv_a; int32_t* adv_b;      /* adversary displacement, 0 when off                   */
+    int32_t* fill_buy; int32_t* fill_sell;
+    int32_t* inventory;                  /* post-step                                            */
+    double* cash; double* reward; double* pnl_reward; double* inventory_reward; double* fee_paid;
+    float* raw_a; float* raw_b;          /* policy outputs before x5 and rounding                */
+} sgmm_trace;
+
+int sgmm_rollout_trace(const sgmm_bundle* bundle, const float* mm_genome, int32_t hidden,
+                       const float* adv_genome, const int32_t* forced_actions,
+                       const sgmm_rollout_params* params, const sgmm_trace* trace,
+                       double* fitness, int32_t* trades, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Scalar env: FTPEnv.step / reset (Env/market_env.py:8-67) for the per-bar Python loops of the
+ * blind test / backtest (pipeline/agent_trainer.py:144-153, pipeline/evaluator.py:25-37).
+ * Host-side instantiation of the same step-core header the kernels use.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    double phi, tick_size, fee_rate;
+    int64_t inventory;
+    double cash;
+    int64_t i_max, i_min;
+} sgmm_env_state;
+
+typedef struct {
+    double reward, pnl_reward, inventory_reward, fee_paid;
+    int32_t fill_buy, fill_sell;
+} sgmm_step_info;
+
+int sgmm_env_init(sgmm_env_state* e, double phi, double tick_size, double fee_rate);
+int sgmm_env_step_host(sgmm_env_state* e, const int64_t action[2], const int64_t* adv_action,
+                       double mid_next, double best_ask, double best_bid,
+                       double buy_max, double sell_min, sgmm_step_info* info);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-side (1,lambda) evolution: NeuroEvolution.ask/tell + the generation loop of
+ * DRLEngine.train (models/model.py:59-76, Env/drl_engine.py:92-171) with no host round trip:
+ *   ask      children are regenerated from (master, sigma, seed, generation, index) in-kernel
+ *   evaluate population rollout on the train bundle (adversary fused when use_arl)
+ *   tell     argmax (first maximum) -> master <- best child; adversary: argmax of -fitness
+ *   validate rollout of the new master on the val bundle, adversary off (:129-140)
+ *   select   keep-best-on-validation snapshot (:144-150), sigma *= 0.5 after `patience`
+ *            non-improving generations (:155-160), history append (:163-167)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sgmm_ga sgmm_ga;
+
+typedef struct {
+    int32_t hidden;           /* H */
+    int32_t use_arl;          /* co-evolve the adversary (Env/drl_engine.py:75,80-81)            */
+    int64_t pop_size;         /* GLOBAL lambda (models/model.py:60)                              */
+    int64_t shard_first;      /* this rank evaluates children [shard_first, shard_first+shard_count) */
+    int64_t shard_count;
+    float sigma;              /* sigma_0 = 0.05 (models/model.py:61)                             */
+    int32_t patience;         /* 15 (Env/drl_engine.py:155)                                      */
+    double phi, fee_rate;
+    uint64_t seed;
+    int32_t max_generations;  /* history capacity                                                */
+    int32_t reserved;
+} sgmm_ga_config;
+
+typedef struct {
+    int32_t generation;       /* generations completed                                           */
+    int32_t stale;            /* non-improving generations since last improvement / decay        */
+    float sigma, adv_sigma;
+    double best_val;
+    int64_t last_best_index;  /* global index of the last generation's best child               */
+} sgmm_ga_status;
+
+/* mm_master / adv_master: HOST float[G] / float[1250] initial masters (adv may be NULL unless use_arl) */
+int sgmm_ga_create(sgmm_ga** out, const sgmm_ga_config* cfg, const float* mm_master,
+                   const float* adv_master, int device, void* stream);
+int sgmm_ga_destroy(sgmm_ga* ga);
+/* DEVICE pointers to this rank's slice of the current generation's results (length shard_count)
+ * and to the full-population gather buffers (length pop_size) that sgmm_ga_select reads.  With
+ * one rank the slice IS the gather buffer.  A multi-GPU caller all-gathers the slices into the
+ * gather buffers between sgmm_ga_evaluate and sgmm_ga_select (NCCL). */
+int sgmm_ga_buffers(sgmm_ga* ga, double** fitness_slice, int32_t** trades_slice,
+                    double** fitness_all, int32_t** trades_all);
+/* phase 1: ask + evaluate this rank's shard on `train` */
+int sgmm_ga_evaluate(sgmm_ga* ga, const sgmm_bundle* train, void* stream);
+/* phase 2: tell + validate on `val` + keep-best + sigma decay + history; advances the generation */
+int sgmm_ga_select(sgmm_ga* ga, const sgmm_bundle* val, void* stream);
+/* both phases back to back (single rank) */
+int sgmm_ga_generation(sgmm_ga* ga, const sgmm_bundle* train, const sgmm_bundle* val, void* stream);
+/* synchronising read-backs (HOST pointers) */
+int sgmm_ga_status_host(sgmm_ga* ga, sgmm_ga_status* status, void* stream);
+int sgmm_ga_master_host(sgmm_ga* ga, float* mm_master, float* adv_master, float* best_val_master,
+                        void* stream);
+/* history columns of Env/drl_engine.py:86-89,163-167; each HOST array of capacity n, may be NULL */
+int sgmm_ga_history_host(sgmm_ga* ga, int32_t n, double* train_f, double* val_f,
+                         int32_t* train_trades, int32_t* val_trades, float* sigma, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helper: sustained FP32 FFMA throughput of the device (TFLOP/s), the denominator of
+ * the H=32 roofline (SURVEY.md section 8d asks for a measured FFMA peak).
+ * ------------------------------------------------------------------------------------------- */
+int sgmm_measure_fp32_peak(int device, double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGMM_H */
