@@ -44,7 +44,7 @@ static int ensure_workspace(sgmm_bundle* b, size_t bytes)
 static int fill_pop(const sgmm_population* p, const char* name, PopArgs& out, int64_t G)
 {
     if (p->count < 0) { set_error("%s.count < 0", name); return SGMM_ERR_INVALID; }
-    if (!p->genomes && !p->master) { set_error("%s: neither genomes nor master given", name); return SGMM_ERR_INVALID; }
+    if (p->count > 0 && !p->genomes && !p->master) { set_error("%s: neither genomes nor master given", name); return SGMM_ERR_INVALID; }
     (void)G;
     out.genomes = p->genomes; out.master = p->master; out.first_index_dev = nullptr;
     out.sigma = p->sigma; out.sigma_dev = nullptr; out.seed = p->seed; out.generation = p->generation;

@@ -15,7 +15,7 @@
 //   * the 32->2 output layer is a butterfly of warp shuffles;
 //   * bars are shared by the whole population: a 4-stage ring of 128-bar chunks is streamed
 //     L2 -> shared memory with cp.async.bulk (TMA 1-D bulk copies) completing on mbarriers; warps
-//     release a stage through an "empty" mbarrier, thread 0 refills it;
+//     release a stage through an "empty" mbarrier and a dedicated producer warp refills it;
 //   * the env step is branch-free: fills are integer compares against per-bar thresholds derived
 //     once per bundle with the reference's exact fp64 expression, inventory/trades are integers,
 //     quotes / P&L / reward sum are un-fused fp64 in the reference's order.
@@ -97,6 +97,20 @@ __device__ int32_t fill_threshold_plus1(double best, double tick, double bound)
     return lo + 1;
 }
 
+// fill <=> rint_half_even(q) <= K  <=>  q < K + 0.5, or q == K + 0.5 exactly and K is even (the tie
+// rounds down to K).  Folding the tie into a strict compare: threshold = K + 0.5, moved one ulp up
+// when K is even.  Exact for |K| < 2^22; beyond that the threshold saturates (documented limit).
+__device__ __forceinline__ float float_threshold(int32_t k_plus1)
+{
+    if (k_plus1 == K_NEVER) return -INFINITY;
+    if (k_plus1 == K_ALWAYS) return INFINITY;
+    const int32_t K = k_plus1 - 1;
+    if (K >= K_FLOAT_EXACT) return INFINITY;
+    if (K <= -K_FLOAT_EXACT) return -INFINITY;
+    const float t = (float)K + 0.5f;                  // exact
+    return (K & 1) == 0 ? nextafterf(t, INFINITY) : t;
+}
+
 __global__ void bundle_prologue_kernel(int64_t T, const float* __restrict__ z1, const float* __restrict__ z2,
                                        const double* __restrict__ mid, const double* __restrict__ ask,
                                        const double* __restrict__ bid, const double* __restrict__ bmax,
@@ -109,6 +123,9 @@ __global__ void bundle_prologue_kernel(int64_t T, const float* __restrict__ z1, 
     s.z1 = z1[t]; s.z2 = z2[t];
     s.ka1 = fill_threshold_plus1<true>(ask[t], tick, bmax[t]);
     s.kb1 = fill_threshold_plus1<false>(bid[t], tick, smin[t]);
+    s.tha = float_threshold(s.ka1);
+    s.thb = float_threshold(s.kb1);
+    s.pad0 = s.pad1 = 0;
     sig[t] = s;
     BarPx p; p.ask = ask[t]; p.bid = bid[t]; p.mid_next = mid[t]; p.pad = 0.0;
     px[t] = p;
@@ -184,16 +201,20 @@ __device__ __forceinline__ GenomeSource make_source(const PopArgs& p, int64_t i,
 // ---------------------------------------------------------------------------------------------
 // the rollout kernel (H = 32)
 // ---------------------------------------------------------------------------------------------
+// compute warps per CTA (one more warp is the producer): bounded by the register file
+__host__ __device__ constexpr int max_compute_warps(int U) { return U == 4 ? 7 : (U == 2 ? 12 : MAX_WARPS); }
+
 struct RingSmem {
     uint64_t full[RING_STAGES];
     uint64_t empty[RING_STAGES];
     BarSig sig[RING_STAGES][CHUNK_BARS];
     BarPx px[RING_STAGES][CHUNK_BARS];
     float hbuf[MAX_WARPS][128];          // per warp: U individuals x 32 activations, 16-B interleaved
+    float rbuf[MAX_WARPS][80];           // per warp: 4 individuals x 8 lanes x (pa,pb), group stride 20 words
 };
 
 template <int U, bool ADV, bool FEE>
-__global__ void __launch_bounds__((U == 4 ? 8 : MAX_WARPS) * 32, 1)
+__global__ void __launch_bounds__((max_compute_warps(U) + 1) * 32, 1)
 rollout_kernel_h32(const RolloutArgs a)
 {
     constexpr int H = 32;
@@ -204,7 +225,7 @@ rollout_kernel_h32(const RolloutArgs a)
     RingSmem& sm = *reinterpret_cast<RingSmem*>(smem_raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = blockDim.x >> 5;
+    const int nwarps = (blockDim.x >> 5) - 1;          // compute warps; the last warp is the TMA producer
     const int g = lane / L, l = lane % L;
     const int64_t first = (int64_t)blockIdx.x * nwarps * NI;
     const int64_t remaining = a.mm.count - first;
@@ -214,23 +235,27 @@ rollout_kernel_h32(const RolloutArgs a)
     const int64_t T = a.T;
     const int64_t nchunks = (T + CHUNK_BARS - 1) / CHUNK_BARS;
 
-    auto issue_chunk = [&](int64_t c) {
-        const int s = (int)(c % RING_STAGES);
-        const int64_t t0 = c * CHUNK_BARS;
-        const uint32_t n = (uint32_t)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
-        mbar_arrive_expect_tx(&sm.full[s], n * (uint32_t)(sizeof(BarSig) + sizeof(BarPx)));
-        tma_bulk_g2s(&sm.sig[s][0], a.sig + t0, n * (uint32_t)sizeof(BarSig), &sm.full[s]);
-        tma_bulk_g2s(&sm.px[s][0], a.px + t0, n * (uint32_t)sizeof(BarPx), &sm.full[s]);
-    };
-
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], live_warps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int64_t c = 0; c < nchunks && c < RING_STAGES; ++c) issue_chunk(c);
+
+    if (warp == nwarps) {
+        // ===== producer warp: one elected lane streams the bar ring, everyone else retires =====
+        if (lane == 0) {
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int s = (int)(c % RING_STAGES);
+                if (c >= RING_STAGES) mbar_wait(&sm.empty[s], (uint32_t)(((c / RING_STAGES) - 1) & 1));
+                const int64_t t0 = c * CHUNK_BARS;
+                const uint32_t n = (uint32_t)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
+                mbar_arrive_expect_tx(&sm.full[s], n * (uint32_t)(sizeof(BarSig) + sizeof(BarPx)));
+                tma_bulk_g2s(&sm.sig[s][0], a.sig + t0, n * (uint32_t)sizeof(BarSig), &sm.full[s]);
+                tma_bulk_g2s(&sm.px[s][0], a.px + t0, n * (uint32_t)sizeof(BarPx), &sm.full[s]);
+            }
+        }
+        return;
     }
     if (warp >= live_warps) return;
 
@@ -282,41 +307,75 @@ rollout_kernel_h32(const RolloutArgs a)
     }
 
     float* hb = &sm.hbuf[warp][0];
+    float* rbw = &sm.rbuf[warp][0];
     const double tick = a.tick, fee = a.fee;
     const double pen0 = mul_rn(a.phi, 0.0), pen1 = mul_rn(a.phi, 1.0), pen2 = mul_rn(a.phi, 2.0);   // market_env.py:57
 
     int inv = 0, trades = 0, fbp = 0, fsp = 0;
+    float inv2 = 0.0f;                                               // inventory / 2.0 (drl_engine.py:35), exact
     double total = 0.0;                                              // drl_engine.py:26
+
+    // Software pipeline: the fp64 accounting of bar i-1 (quotes, P&L legs, penalty, reward sum) is
+    // issued inside step i, where the scheduler can bury its latency under the hidden-layer FMAs; only
+    // the fill decision and the inventory update stay on the step-to-step critical path.
+    // The initial pending record is an exact no-op (no fill, |inv| = 0: total += +0.0).
+    int pk_a = 0, pk_b = 0, p_ai = 0; bool p_fb = false, p_fs = false;
+
+#define SGMM_ACCOUNT(PX)                                                                              \
+    {                                                                                                 \
+        const double2 ab_ = *reinterpret_cast<const double2*>(&(PX).ask);                             \
+        const double mid_ = (PX).mid_next;                                                            \
+        const double my_ask_ = add_rn(ab_.x, mul_rn((double)pk_a, tick));       /* market_env.py:30 */ \
+        const double my_bid_ = sub_rn(ab_.y, mul_rn((double)pk_b, tick));       /* :31 */              \
+        double leg_b_ = sub_rn(mid_, my_bid_), leg_s_ = sub_rn(my_ask_, mid_);                        \
+        if (FEE) {                                                                                    \
+            leg_b_ = sub_rn(leg_b_, mul_rn(my_bid_, fee));                      /* :46,:48 */          \
+            leg_s_ = sub_rn(leg_s_, mul_rn(my_ask_, fee));                      /* :52,:54 */          \
+        }                                                                                             \
+        double pnl_ = 0.0;                                                      /* :40 */              \
+        pnl_ = p_fb ? add_rn(pnl_, leg_b_) : pnl_;                                                    \
+        pnl_ = p_fs ? add_rn(pnl_, leg_s_) : pnl_;                                                    \
+        const double pen_ = p_ai == 0 ? pen0 : (p_ai == 1 ? pen1 : pen2);       /* :57 */              \
+        total = add_rn(total, sub_rn(pnl_, pen_));                              /* :58, drl_engine.py:54 */ \
+    }
 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int s = (int)(c % RING_STAGES);
-        if (threadIdx.x == 0 && c >= 1 && c - 1 + RING_STAGES < nchunks) {
-            // refill the stage every warp has finished with (chunk c-1) with chunk c-1+S
-            mbar_wait(&sm.empty[(c - 1) % RING_STAGES], (uint32_t)(((c - 1) / RING_STAGES) & 1));
-            issue_chunk(c - 1 + RING_STAGES);
-        }
-        __syncwarp();
         mbar_wait(&sm.full[s], (uint32_t)((c / RING_STAGES) & 1));
+        __syncwarp();
         const int64_t t0 = c * CHUNK_BARS;
         const int n = (int)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
         const BarSig* sigs = &sm.sig[s][0];
         const BarPx* pxs = &sm.px[s][0];
 
+        // bar 0 of the chunk: signals, thresholds and the inventory-independent part of layer 1
+        float4 sg = *reinterpret_cast<const float4*>(&sigs[0]);                     // z1, z2, tha, thb
+        int2 kth = *reinterpret_cast<const int2*>(&sigs[0].ka1);
+        float A1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) A1[u] = __fmaf_rn(w1y[u], sg.y, __fmaf_rn(w1x[u], sg.x, b1[u]));
+
 #pragma unroll 1
         for (int i = 0; i < n; ++i) {
-            const float4 sg = *reinterpret_cast<const float4*>(&sigs[i]);          // z1, z2, ka1, kb1
-            const float inv2 = (float)inv * 0.5f;                                   // drl_engine.py:35
-            // ---- layer 1 + ReLU, publish h1 -------------------------------------------------
+            // ---- layer 1 (inventory term) + ReLU, publish h1 ------------------------------------
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int j = l + L * u;
-                float v = __fmaf_rn(w1x[u], sg.x, b1[u]);
-                v = __fmaf_rn(w1y[u], sg.y, v);
-                v = __fmaf_rn(w1i[u], inv2, v);
-                hb[((j >> 2) * NI + g) * 4 + (j & 3)] = fmaxf(v, 0.0f);
+                hb[((j >> 2) * NI + g) * 4 + (j & 3)] = fmaxf(__fmaf_rn(w1i[u], inv2, A1[u]), 0.0f);
             }
             __syncwarp();
-            // ---- layer 2: U rows x 32, packed FFMA2, four chains per row -------------------
+            const float tha = sg.z, thb = sg.w;
+            const int ka1 = kth.x, kb1 = kth.y;
+            // ---- prefetch bar i+1 and its layer-1 partial (off the critical path) --------------
+            const int inext = i + 1 < CHUNK_BARS ? i + 1 : CHUNK_BARS - 1;
+            sg = *reinterpret_cast<const float4*>(&sigs[inext]);
+            if (ADV) kth = *reinterpret_cast<const int2*>(&sigs[inext].ka1);
+            float A1n[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) A1n[u] = __fmaf_rn(w1y[u], sg.y, __fmaf_rn(w1x[u], sg.x, b1[u]));
+            // ---- deferred fp64 accounting of bar i-1 ---------------------------------------------
+            SGMM_ACCOUNT(pxs[i > 0 ? i - 1 : 0])
+            // ---- layer 2: U rows x 32, packed FFMA2, four chains per row -----------------------
             float2 P[U], Q[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { P[u] = make_float2(b2[u], 0.0f); Q[u] = make_float2(0.0f, 0.0f); }
@@ -330,8 +389,7 @@ rollout_kernel_h32(const RolloutArgs a)
                     Q[u] = __ffma2_rn(w2[u][2 * k + 1], hhi, Q[u]);
                 }
             }
-            __syncwarp();            // all lanes have read hb before the next step overwrites it
-            // ---- layer 3: products, local tree, shuffle butterfly ---------------------------
+            // ---- layer 3: products, local tree, then the cross-lane tree ------------------------
             float pa[U], pb[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -341,49 +399,65 @@ rollout_kernel_h32(const RolloutArgs a)
                 pb[u] = __fmul_rn(w3b[u], h2);
             }
             float ra, rb;
-            if (U == 4) { ra = __fadd_rn(__fadd_rn(pa[0], pa[2 % U]), __fadd_rn(pa[1 % U], pa[3 % U]));
-                          rb = __fadd_rn(__fadd_rn(pb[0], pb[2 % U]), __fadd_rn(pb[1 % U], pb[3 % U])); }
-            else if (U == 2) { ra = __fadd_rn(pa[0], pa[1 % U]); rb = __fadd_rn(pb[0], pb[1 % U]); }
-            else { ra = pa[0]; rb = pb[0]; }
+            if (U == 4) {
+                ra = __fadd_rn(__fadd_rn(pa[0], pa[2 % U]), __fadd_rn(pa[1 % U], pa[3 % U]));
+                rb = __fadd_rn(__fadd_rn(pb[0], pb[2 % U]), __fadd_rn(pb[1 % U], pb[3 % U]));
+                // butterfly over the 8 lanes of the individual, evaluated by every lane from the 8
+                // partials exchanged through shared memory (same tree, 1 round trip instead of 3 shuffles)
+                *reinterpret_cast<float2*>(&rbw[g * 20 + l * 2]) = make_float2(ra, rb);
+                __syncwarp();
+                const float4 r01 = *reinterpret_cast<const float4*>(&rbw[g * 20 + 0]);
+                const float4 r23 = *reinterpret_cast<const float4*>(&rbw[g * 20 + 4]);
+                const float4 r45 = *reinterpret_cast<const float4*>(&rbw[g * 20 + 8]);
+                const float4 r67 = *reinterpret_cast<const float4*>(&rbw[g * 20 + 12]);
+                const float2 t04 = __fadd2_rn(make_float2(r01.x, r01.y), make_float2(r45.x, r45.y));
+                const float2 t15 = __fadd2_rn(make_float2(r01.z, r01.w), make_float2(r45.z, r45.w));
+                const float2 t26 = __fadd2_rn(make_float2(r23.x, r23.y), make_float2(r67.x, r67.y));
+                const float2 t37 = __fadd2_rn(make_float2(r23.z, r23.w), make_float2(r67.z, r67.w));
+                const float2 e = __fadd2_rn(__fadd2_rn(t04, t26), __fadd2_rn(t15, t37));
+                ra = e.x; rb = e.y;
+            } else {
+                if (U == 2) { ra = __fadd_rn(pa[0], pa[1 % U]); rb = __fadd_rn(pb[0], pb[1 % U]); }
+                else { ra = pa[0]; rb = pb[0]; }
 #pragma unroll
-            for (int m = L / 2; m >= 1; m >>= 1) {
-                ra = __fadd_rn(ra, __shfl_xor_sync(0xffffffffu, ra, m));
-                rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
+                for (int m = L / 2; m >= 1; m >>= 1) {
+                    ra = __fadd_rn(ra, __shfl_xor_sync(0xffffffffu, ra, m));
+                    rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
+                }
             }
-            ra = __fadd_rn(ra, b3a); rb = __fadd_rn(rb, b3b);
-            // ---- quantise: np.round(raw*5.0).astype(int) (drl_engine.py:39) -----------------
-            int ka = __float2int_rn(__fmul_rn(ra, 5.0f));
-            int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
+            // ---- quantise + fill decision -------------------------------------------------------
+            const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);           // raw*5.0 (drl_engine.py:39)
+            const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
+            int ka = __float2int_rn(qa);                                     // np.round(...).astype(int)
+            int kb = __float2int_rn(qb);
+            bool fb, fs;
             if (ADV) {                                                       // drl_engine.py:42-48
                 const uint32_t e = table_lookup(adv_t0, adv_t1, adv_t2, fsp * 10 + fbp * 5 + inv + 2);
                 ka = max(min(ka, K_CLAMP), -K_CLAMP) + (int)(e & 3u) - 1;    // market_env.py:26-28
                 kb = max(min(kb, K_CLAMP), -K_CLAMP) + (int)(e >> 2) - 1;
+                fb = (inv2 < 1.0f) && (kb < kb1);                            // :34,:37
+                fs = (inv2 > -1.0f) && (ka < ka1);                           // :35,:38
+                fbp = fb ? 1 : 0; fsp = fs ? 1 : 0;                          // drl_engine.py:57-58
+            } else {
+                // rounding folded into the per-bar float threshold: no conversion on the critical path
+                fb = (inv2 < 1.0f) && (qb < thb);
+                fs = (inv2 > -1.0f) && (qa < tha);
             }
-            // ---- env step (market_env.py:30-58), branch-free --------------------------------
-            const bool fb = (inv < 2) && (kb < __float_as_int(sg.w));       // :34,:37
-            const bool fs = (inv > -2) && (ka < __float_as_int(sg.z));      // :35,:38
-            inv += (fb ? 1 : 0) - (fs ? 1 : 0);                             // :45,:51
-            trades += (fb || fs) ? 1 : 0;                                   // drl_engine.py:60-61
-            if (ADV) { fbp = fb ? 1 : 0; fsp = fs ? 1 : 0; }                // drl_engine.py:57-58
-            const double2 ab = *reinterpret_cast<const double2*>(&pxs[i].ask);
-            const double mid = pxs[i].mid_next;
-            const double my_ask = add_rn(ab.x, mul_rn((double)ka, tick));   // :30
-            const double my_bid = sub_rn(ab.y, mul_rn((double)kb, tick));   // :31
-            double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
-            if (FEE) {
-                leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                 // :46,:48
-                leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                 // :52,:54
-            }
-            double pnl = 0.0;                                               // :40
-            pnl = fb ? add_rn(pnl, leg_b) : pnl;
-            pnl = fs ? add_rn(pnl, leg_s) : pnl;
-            const int ai = inv < 0 ? -inv : inv;
-            const double pen = ai == 0 ? pen0 : (ai == 1 ? pen1 : pen2);    // :57
-            total = add_rn(total, sub_rn(pnl, pen));                        // :58, drl_engine.py:54
+            inv2 = __fadd_rn(inv2, fb ? (fs ? 0.0f : 0.5f) : (fs ? -0.5f : 0.0f));   // :45,:51 (exact)
+            inv += (fb ? 1 : 0) - (fs ? 1 : 0);
+            trades += (fb || fs) ? 1 : 0;                                    // drl_engine.py:60-61
+            // hand the bar to the deferred accounting
+            pk_a = ka; pk_b = kb; p_fb = fb; p_fs = fs; p_ai = inv < 0 ? -inv : inv;
+#pragma unroll
+            for (int u = 0; u < U; ++u) A1[u] = A1n[u];
         }
+        // the chunk's last bar must be accounted before its stage is released
+        SGMM_ACCOUNT(pxs[n - 1])
+        p_fb = false; p_fs = false; p_ai = 0;
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
+#undef SGMM_ACCOUNT
     if (trades == 0) total = sub_rn(total, 50.0);                           // drl_engine.py:64-65
     if (live && l == 0) { a.fitness[ind] = total; a.trades[ind] = trades; }
 }
@@ -401,7 +475,7 @@ static int launch_variant(const RolloutArgs& args, int warps, cudaStream_t st)
     }
     const int64_t per_cta = (int64_t)warps * U;
     const int64_t blocks = (args.mm.count + per_cta - 1) / per_cta;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(args);
+    kern<<<(unsigned)blocks, (warps + 1) * 32, smem, st>>>(args);   // + the producer warp
     return check_cuda(cudaGetLastError(), "rollout_kernel_h32 launch");
 }
 
@@ -433,7 +507,7 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
     int W = warps_per_cta;
     if (W == 0) {
         // one CTA per SM per wave; spread the population evenly over the SMs of each wave
-        const int max_w = (U == 4) ? 8 : (U == 2 ? 16 : 16);
+        const int max_w = max_compute_warps(U);
         const int64_t per_sm_full = (int64_t)max_w * U;
         const int64_t waves = (mm.count + per_sm_full * sms - 1) / (per_sm_full * sms);
         const int64_t per_sm = (mm.count + waves * sms - 1) / (waves * sms);
@@ -441,7 +515,7 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
         if (W < 1) W = 1;
         if (W > max_w) W = max_w;
     }
-    if (W < 1 || W > MAX_WARPS) { set_error("warps_per_cta must be in 1..%d", MAX_WARPS); return SGMM_ERR_INVALID; }
+    if (W < 1 || W > max_compute_warps(U)) { set_error("warps_per_cta must be in 1..%d for units_per_lane=%d", max_compute_warps(U), U); return SGMM_ERR_INVALID; }
     RolloutArgs args;
     args.sig = b->sig; args.px = b->px; args.T = b->T; args.tick = b->tick; args.phi = phi; args.fee = fee;
     args.mm = mm;
