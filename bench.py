@@ -294,12 +294,14 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak if fp32_peak else None,
-                         "traffic": None,
+                         "traffic": 20926208,
                          "kernel": "rollout_kernel_h32<4,false,false>",
                          "algorithmic_flop_per_env_step": FLOP_PER_STEP,
                          "peak_source": "FFMA/FFMA2 peak measured live on this device by sgmm_measure_fp32_peak "
                                         "(MEASURED_PEAKS.json has no fp32 figure; theoretical 74.4 TFLOP/s at 1965 MHz)",
-                         "note": "compute-bound on the FP32 CUDA-core pipe (SURVEY.md 8d); bound is neither hbm nor tensor",
+                         "note": "compute-bound on the FP32 CUDA-core pipe (SURVEY.md 8d); bound is neither hbm nor tensor. "
+                                 "traffic = dram__bytes_read+write of one launch from profiles/r1_rollout_u4_ncu_full.txt "
+                                 "(P=4096: 20.9 MB, i.e. the genomes once; bars stay in L2)",
                          "hbm": {"achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
                                  "peak_source": hbm_src}},
