@@ -176,7 +176,11 @@ static int check_rollout_args(const sgmm_bundle* bundle, const sgmm_population* 
 {
     if (!bundle || !mm || !params) { set_error("NULL bundle / mm / params"); return SGMM_ERR_INVALID; }
     if (mm->count > 0 && (!fitness || !trades)) { set_error("NULL output array"); return SGMM_ERR_INVALID; }
-    if (params->precision != SGMM_PRECISION_F32) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
+    if (params->precision != SGMM_PRECISION_F32 && params->precision != SGMM_PRECISION_BF16) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
+    if (mm->hidden == 256) {
+        if (params->precision != SGMM_PRECISION_BF16) { set_error("hidden=256 runs on the tensor cores: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 path is built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
+        if (adv) { set_error("the H=256 tensor-core rollout has no adversary path"); return SGMM_ERR_UNSUPPORTED; }
+    } else if (params->precision != SGMM_PRECISION_F32) { set_error("precision=SGMM_PRECISION_BF16 needs hidden=256"); return SGMM_ERR_UNSUPPORTED; }
     if (adv && adv->count != mm->count) { set_error("adv.count (%lld) != mm.count (%lld): MM i meets adversary i (Env/drl_engine.py:115)", (long long)adv->count, (long long)mm->count); return SGMM_ERR_INVALID; }
     if (adv && adv->hidden != 32) { set_error("adversary genomes are 1250-float TradingPolicy(32) genomes (models/model.py:63)"); return SGMM_ERR_INVALID; }
     return SGMM_OK;
@@ -190,8 +194,21 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
     if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
     if (adv) if (int rc = fill_pop(adv, "adv", pa, 1250)) return rc;
     DeviceGuard guard(bundle->device);
+    if (mm->hidden == 256)
+        return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
     return launch_rollout(bundle, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                           params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
+}
+
+int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_rollout_params* params,
+                               double* fitness, int32_t* trades, float* raw_table, int32_t* act_trace, void* stream)
+{
+    if (int rc = check_rollout_args(bundle, mm, nullptr, params, fitness, trades)) return rc;
+    if (mm->hidden != 256) { set_error("audit entry is for hidden=256"); return SGMM_ERR_INVALID; }
+    PopArgs pm;
+    if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
+    DeviceGuard guard(bundle->device);
+    return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
 }
 
 int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
@@ -223,8 +240,10 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
         if (int rc = check_cuda(cudaMemcpyAsync(d_adv, asrc, (size_t)(adv->genomes ? P * GA : GA) * sizeof(float), cudaMemcpyHostToDevice, st), "H2D adversary genomes")) return rc;
         if (adv->genomes) pa.genomes = d_adv; else pa.master = d_adv;
     }
-    if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
-                                params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
+    if (mm->hidden == 256) {
+        if (int rc = launch_spec256(b, pm, params->phi, params->fee_rate, d_fit, d_trd, nullptr, nullptr, st)) return rc;
+    } else if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
+                                       params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
     if (int rc = check_cuda(cudaMemcpyAsync(fitness, d_fit, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H fitness")) return rc;
     if (int rc = check_cuda(cudaMemcpyAsync(trades, d_trd, (size_t)P * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "D2H trades")) return rc;
     return check_cuda(cudaStreamSynchronize(st), "rollout_population_host");

@@ -77,6 +77,8 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
 int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const float* adv_genome,
                  const int32_t* forced, double phi, double fee, const sgmm_trace* tr,
                  double* fitness, int32_t* trades, cudaStream_t st);
+int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades,
+                   float* raw_table, int32_t* act_trace, cudaStream_t st);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,
                     const double* ask, const double* bid, cudaStream_t st);
 

@@ -29,8 +29,13 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _params(phi, fee_rate, units_per_lane=0, warps_per_cta=0):
-    return _lib.RolloutParams(float(phi), float(fee_rate), 0, 0, int(units_per_lane), int(warps_per_cta))
+PRECISION_F32, PRECISION_BF16 = 0, 1
+
+
+def _params(phi, fee_rate, units_per_lane=0, warps_per_cta=0, hidden=32):
+    """hidden=32 -> bit-exact SGMM-F32 path; hidden=256 -> tcgen05 tensor-core path (bf16 inputs)."""
+    prec = PRECISION_BF16 if hidden == 256 else PRECISION_F32
+    return _lib.RolloutParams(float(phi), float(fee_rate), prec, 0, int(units_per_lane), int(warps_per_cta))
 
 
 def _as_f32_matrix(x, width):
@@ -65,7 +70,7 @@ def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_ra
     L = _lib.lib()
     mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
     adv = None if a is None else _lib.Population(32, 0, P, a.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
-    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta)
+    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta, hidden)
     advp = None if adv is None else C.byref(adv)
     if g.is_cuda:
         if g.device.index != bundle.device or (a is not None and a.device != g.device):
@@ -107,10 +112,27 @@ def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, fi
         adv = _lib.Population(32, 0, count, None, am.data_ptr(), float(sigma if adv_sigma is None else adv_sigma),
                               0.0, int(seed) ^ ADV_SEED_FLIP, int(generation), int(first_index))
         advp = C.byref(adv)
-    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta)
+    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta, hidden)
     _lib.check(_lib.lib().sgmm_rollout_population(bundle.handle, C.byref(mm), advp, C.byref(prm),
                                                   fit.data_ptr(), trd.data_ptr(), _stream(bundle.device)))
     return fit, trd
+
+
+def rollout_spec256_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0):
+    """Tensor-core (H=256, bf16) rollout with its audit outputs: returns ``(fitness, trades,
+    raw_table float32[P,T,5,2], act_trace int32[P,T,2])`` as CUDA tensors."""
+    g = _as_f32_matrix(genomes, genome_len(256)).to(f"cuda:{bundle.device}")
+    P, T = g.shape[0], bundle.T
+    fit = torch.empty(P, dtype=torch.float64, device=g.device)
+    trd = torch.empty(P, dtype=torch.int32, device=g.device)
+    raw = torch.zeros(P, T, 5, 2, dtype=torch.float32, device=g.device)
+    act = torch.zeros(P, T, 2, dtype=torch.int32, device=g.device)
+    mm = _lib.Population(256, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    prm = _params(phi, fee_rate, hidden=256)
+    _lib.check(_lib.lib().sgmm_rollout_spec256_audit(bundle.handle, C.byref(mm), C.byref(prm), fit.data_ptr(),
+                                                     trd.data_ptr(), raw.data_ptr(), act.data_ptr(),
+                                                     _stream(bundle.device)))
+    return fit, trd, raw, act
 
 
 _TRACE_I32 = ("off_a", "off_b", "adv_a", "adv_b", "fill_buy", "fill_sell", "inventory")

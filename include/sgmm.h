@@ -41,7 +41,9 @@ extern "C" {
 #define SGMM_ERR_UNSUPPORTED -4     /* device is not sm_100 class / feature not built                */
 
 /* precision of the policy MLP */
-#define SGMM_PRECISION_F32   0      /* SGMM-F32 order on CUDA cores: bit-identical to the oracle     */
+#define SGMM_PRECISION_F32   0      /* SGMM-F32 order on CUDA cores: bit-identical to the oracle (H=32) */
+#define SGMM_PRECISION_BF16  1      /* hidden layer on tcgen05 tensor cores, bf16 x bf16 -> fp32 in   */
+                                    /* TMEM, all 5 inventories of every bar evaluated at once (H=256) */
 
 /* rollout flags */
 #define SGMM_FLAG_NONE       0
@@ -121,6 +123,15 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
 int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_population* mm,
                                  const sgmm_population* adv, const sgmm_rollout_params* params,
                                  double* fitness, int32_t* trades, void* stream);
+
+/* Audit variant of the tensor-core path (hidden = 256, SGMM_PRECISION_BF16): same kernel, plus
+ *   raw_table  DEVICE float[count][T][5][2]  policy outputs for every (bar, inventory -2..2)
+ *   act_trace  DEVICE int32[count][T][2]     the offsets actually taken along the walked trajectory
+ * (either may be NULL).  Used to state the bf16 tolerance against the fp32 oracle and to replay the
+ * taken actions through the oracle's env bit for bit. */
+int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population* mm,
+                               const sgmm_rollout_params* params, double* fitness, int32_t* trades,
+                               float* raw_table, int32_t* act_trace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-step trace of ONE individual: the recorder row contract (Env/recorder.py:8-36,
