@@ -255,7 +255,16 @@ int sgmm_rollout_trace(const sgmm_bundle* bundle, const float* mm_genome, int32_
 {
     if (!bundle || !params) { set_error("NULL bundle / params"); return SGMM_ERR_INVALID; }
     DeviceGuard guard(bundle->device);
-    return launch_trace(bundle, mm_genome, hidden, adv_genome, forced_actions, params->phi, params->fee_rate,
+    return launch_trace(bundle, mm_genome, hidden, adv_genome, forced_actions, nullptr, params->phi, params->fee_rate,
+                        trace, fitness, trades, (cudaStream_t)stream);
+}
+
+int sgmm_rollout_table(const sgmm_bundle* bundle, const int32_t* table, const sgmm_rollout_params* params,
+                       const sgmm_trace* trace, double* fitness, int32_t* trades, void* stream)
+{
+    if (!bundle || !params || !table) { set_error("NULL bundle / params / table"); return SGMM_ERR_INVALID; }
+    DeviceGuard guard(bundle->device);
+    return launch_trace(bundle, nullptr, 32, nullptr, nullptr, table, params->phi, params->fee_rate,
                         trace, fitness, trades, (cudaStream_t)stream);
 }
 

@@ -75,7 +75,7 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
                    double phi, double fee, int units_per_lane, int warps_per_cta,
                    double* fitness, int32_t* trades, cudaStream_t st);
 int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const float* adv_genome,
-                 const int32_t* forced, double phi, double fee, const sgmm_trace* tr,
+                 const int32_t* forced, const int32_t* table, double phi, double fee, const sgmm_trace* tr,
                  double* fitness, int32_t* trades, cudaStream_t st);
 int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades,
                    float* raw_table, int32_t* act_trace, cudaStream_t st);

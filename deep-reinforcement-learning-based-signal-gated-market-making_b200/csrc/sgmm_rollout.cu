@@ -537,7 +537,7 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
 struct TraceArgs {
     const BarSig* sig; const BarPx* px; const double* bmax; const double* smin;
     int64_t T; double tick, phi, fee;
-    const float* mm; const float* adv; const int32_t* forced;
+    const float* mm; const float* adv; const int32_t* forced; const int32_t* table;
     sgmm_trace tr; double* fitness; int32_t* trades;
 };
 
@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(32, 1) trace_kernel_h32(const TraceArgs a)
         const float inv2 = (float)((int)env.inventory) * 0.5f;
         float ra = 0.0f, rb = 0.0f; int ka, kb;
         if (a.forced) { ka = a.forced[2 * t]; kb = a.forced[2 * t + 1]; }
+        else if (a.table) { const int64_t r = (t * 5 + (int)env.inventory + 2) * 2; ka = a.table[r]; kb = a.table[r + 1]; }
         else {
             float v = __fmaf_rn(w1x, sg.z1, b1);
             v = __fmaf_rn(w1y, sg.z2, v);
@@ -635,14 +636,14 @@ __global__ void __launch_bounds__(32, 1) trace_kernel_h32(const TraceArgs a)
 }
 
 int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const float* adv_genome,
-                 const int32_t* forced, double phi, double fee, const sgmm_trace* tr,
+                 const int32_t* forced, const int32_t* table, double phi, double fee, const sgmm_trace* tr,
                  double* fitness, int32_t* trades, cudaStream_t st)
 {
     if (hidden != 32) { set_error("hidden=%d: the trace kernel is built for H=32", hidden); return SGMM_ERR_UNSUPPORTED; }
-    if (!mm_genome && !forced) { set_error("trace needs a genome or forced actions"); return SGMM_ERR_INVALID; }
+    if (!mm_genome && !forced && !table) { set_error("trace needs a genome, forced actions or an inventory table"); return SGMM_ERR_INVALID; }
     TraceArgs a;
     a.sig = b->sig; a.px = b->px; a.bmax = b->bmax; a.smin = b->smin; a.T = b->T;
-    a.tick = b->tick; a.phi = phi; a.fee = fee; a.mm = mm_genome; a.adv = adv_genome; a.forced = forced;
+    a.tick = b->tick; a.phi = phi; a.fee = fee; a.mm = mm_genome; a.adv = adv_genome; a.forced = forced; a.table = table;
     if (tr) a.tr = *tr; else { sgmm_trace z = {}; a.tr = z; }
     a.fitness = fitness; a.trades = trades;
     trace_kernel_h32<<<1, 32, 0, st>>>(a);

@@ -226,29 +226,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
             for (int64_t it = 0; it < ntiles; ++it) {
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
+                // bar data of this row's step: issued before the accumulator is even ready so that the
+                // L2 latency hides behind the MMA wait and the column loop
+                const int64_t t = it * TILE_BARS + tl;
+                const bool valid = (row < TILE_BARS * 5) && (t < T);
+                const int64_t tc_ = valid ? t : 0;
+                const int2 kth = T > 0 ? __ldg(reinterpret_cast<const int2*>(&a.sig[tc_].ka1)) : make_int2(0, 0);
+                const double2 ab = T > 0 ? __ldg(reinterpret_cast<const double2*>(&a.px[tc_].ask)) : make_double2(0., 0.);
+                const double mid = T > 0 ? __ldg(&a.px[tc_].mid_next) : 0.0;
+
                 mbar_wait(&sm.d_full[buf], use & 1u);
                 tc_fence_after();
-                float2 accA[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-                float2 accB[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll 1
+                float2 accA[4], accB[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { accA[q] = make_float2(0.f, 0.f); accB[q] = make_float2(0.f, 0.f); }
+                const uint32_t tbase = lane_addr + buf * 256u;
+                uint32_t v[2][32];
+                tmem_ld32(tbase, v[0]);
+#pragma unroll
                 for (int cc = 0; cc < H / 32; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + buf * 256u + (uint32_t)(cc * 32), v);
-                    tmem_ld_wait();
+                    tmem_ld_wait();                                        // chunk cc has landed
+                    if (cc + 1 < H / 32) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
+                    const uint32_t* w = v[cc & 1];
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
                         const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cc * 32 + c]);
                         const float4 wa = *reinterpret_cast<const float4*>(&sm.w3a[cc * 32 + c]);
                         const float4 wb = *reinterpret_cast<const float4*>(&sm.w3b[cc * 32 + c]);
-                        float2 x0 = __fadd2_rn(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), make_float2(bb.x, bb.y));
-                        float2 x1 = __fadd2_rn(make_float2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])), make_float2(bb.z, bb.w));
+                        float2 x0 = __fadd2_rn(make_float2(__uint_as_float(w[c]), __uint_as_float(w[c + 1])), make_float2(bb.x, bb.y));
+                        float2 x1 = __fadd2_rn(make_float2(__uint_as_float(w[c + 2]), __uint_as_float(w[c + 3])), make_float2(bb.z, bb.w));
                         x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f);
-                        accA[0] = __ffma2_rn(x0, make_float2(wa.x, wa.y), accA[0]);
-                        accB[0] = __ffma2_rn(x0, make_float2(wb.x, wb.y), accB[0]);
-                        accA[1] = __ffma2_rn(x1, make_float2(wa.z, wa.w), accA[1]);
-                        accB[1] = __ffma2_rn(x1, make_float2(wb.z, wb.w), accB[1]);
+                        const int q = (c >> 2) & 1;
+                        accA[2 * q] = __ffma2_rn(x0, make_float2(wa.x, wa.y), accA[2 * q]);
+                        accB[2 * q] = __ffma2_rn(x0, make_float2(wb.x, wb.y), accB[2 * q]);
+                        accA[2 * q + 1] = __ffma2_rn(x1, make_float2(wa.z, wa.w), accA[2 * q + 1]);
+                        accB[2 * q + 1] = __ffma2_rn(x1, make_float2(wb.z, wb.w), accB[2 * q + 1]);
                     }
                 }
+                accA[0] = __fadd2_rn(accA[0], accA[2]); accA[1] = __fadd2_rn(accA[1], accA[3]);
+                accB[0] = __fadd2_rn(accB[0], accB[2]); accB[1] = __fadd2_rn(accB[1], accB[3]);
                 // the accumulator has been read: hand the TMEM buffer back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
@@ -259,18 +275,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));          // drl_engine.py:39
                 const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
                 // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                const int64_t t = it * TILE_BARS + tl;
                 TableEntry e;
                 e.ka = ka; e.kb = kb; e.raw_a = ra; e.raw_b = rb; e.reward = 0.0; e.next = iv; e.traded = 0;
-                if (row < TILE_BARS * 5 && t < T) {
-                    const BarSig sg = a.sig[t];
-                    const BarPx px = a.px[t];
+                if (valid) {
                     const int inv = iv - 2;
-                    const bool fb = (inv < 2) && (kb < sg.kb1);              // :34,:37
-                    const bool fs = (inv > -2) && (ka < sg.ka1);             // :35,:38
-                    const double my_ask = add_rn(px.ask, mul_rn((double)ka, a.tick));
-                    const double my_bid = sub_rn(px.bid, mul_rn((double)kb, a.tick));
-                    double leg_b = sub_rn(px.mid_next, my_bid), leg_s = sub_rn(my_ask, px.mid_next);
+                    const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
+                    const bool fs = (inv > -2) && (ka < kth.x);              // :35,:38
+                    const double my_ask = add_rn(ab.x, mul_rn((double)ka, a.tick));
+                    const double my_bid = sub_rn(ab.y, mul_rn((double)kb, a.tick));
+                    double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
                     if (FEE) {
                         leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
                         leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));

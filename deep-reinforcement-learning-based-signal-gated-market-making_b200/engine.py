@@ -171,6 +171,26 @@ def rollout_trace(bundle: Bundle, genome=None, adv_genome=None, forced_actions=N
     return float(fit.item()), int(trd.item()), out
 
 
+def rollout_table(bundle: Bundle, table, *, phi, fee_rate=0.0):
+    """Walk an inventory-indexed offset table int32[T,5,2] (FOIC / GLFT benchmarks, see
+    :mod:`benchmarks`) through the device step core.  Returns ``(fitness, trades, trace dict)``."""
+    dev = torch.device(f"cuda:{bundle.device}")
+    T = bundle.T
+    tab = torch.as_tensor(np.ascontiguousarray(table, np.int32)).reshape(-1).to(dev).contiguous()
+    if tab.numel() != T * 10:
+        raise ValueError("table must be [T, 5, 2]")
+    cols = {k: torch.zeros(T, dtype=torch.int32, device=dev) for k in _TRACE_I32}
+    cols.update({k: torch.zeros(T, dtype=torch.float64, device=dev) for k in _TRACE_F64})
+    cols.update({k: torch.zeros(T, dtype=torch.float32, device=dev) for k in _TRACE_F32})
+    tr = _lib.Trace(*[cols[n].data_ptr() for n, _ in _lib.Trace._fields_])
+    fit = torch.zeros(1, dtype=torch.float64, device=dev)
+    trd = torch.zeros(1, dtype=torch.int32, device=dev)
+    prm = _params(phi, fee_rate)
+    _lib.check(_lib.lib().sgmm_rollout_table(bundle.handle, tab.data_ptr(), C.byref(prm), C.byref(tr),
+                                             fit.data_ptr(), trd.data_ptr(), _stream(bundle.device)))
+    return float(fit.item()), int(trd.item()), {k: v.cpu().numpy() for k, v in cols.items()}
+
+
 def measure_fp32_peak(device=0) -> float:
     """Sustained FP32 FMA TFLOP/s of the device (roofline denominator for H=32)."""
     v = C.c_double()

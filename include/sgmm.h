@@ -153,6 +153,11 @@ int sgmm_rollout_trace(const sgmm_bundle* bundle, const float* mm_genome, int32_
                        const sgmm_rollout_params* params, const sgmm_trace* trace,
                        double* fitness, int32_t* trades, void* stream);
 
+/* Inventory-table policies (benchmarks FOIC / GLFT, Env/benchmarks.py:3-40 driven by main.py:99-132):
+ * the action at bar t is table[t][inv+2][{a,b}] (DEVICE int32[T,5,2]); same step core, same trace. */
+int sgmm_rollout_table(const sgmm_bundle* bundle, const int32_t* table, const sgmm_rollout_params* params,
+                       const sgmm_trace* trace, double* fitness, int32_t* trades, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Scalar env: FTPEnv.step / reset (Env/market_env.py:8-67) for the per-bar Python loops of the
  * blind test / backtest (pipeline/agent_trainer.py:144-153, pipeline/evaluator.py:25-37).

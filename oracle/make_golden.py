@@ -207,6 +207,46 @@ def ref_rollouts():
     print("ref_rollouts.npz", len(out), "arrays;", "T0 ->", f0, n0, " T1 ->", f1, n1)
 
 
+def benchmark_policies():
+    """FOIC / GLFT through the reference's own FTPEnv and Env/benchmarks.py classes with the driver
+    loop of main.py:99-132 re-typed (main.py itself needs seaborn/statsmodels and the un-shipped data)."""
+    from Env.benchmarks import FOICPolicy, GLFTPolicy
+    out = {}
+    bundle = synth.synthetic_bundle(2, first_day=11)
+    s1, s2, mid, ask, bid, b_max, s_min = bundle
+    for k, v in zip(("s1", "s2", "mid_next", "best_ask", "best_bid", "buy_max", "sell_min"), bundle):
+        out[f"bundle.{k}"] = v
+    pols = {"glft": GLFTPolicy(gamma=0.0001, kappa=3000, A=0.1, sigma=0.0005),       # main.py:206
+            "glft_wide": GLFTPolicy(gamma=0.01, kappa=1500, A=0.1, sigma=0.02),
+            "foic": FOICPolicy(offset_a=0, offset_b=0),                               # main.py:209
+            "foic_1_2": FOICPolicy(offset_a=1, offset_b=2)}
+    for name, policy in pols.items():
+        for fee in (0.0, 3e-4):
+            env = FTPEnv(phi=1e-4, tick_size=0.001, fee_rate=fee)
+            T = len(mid)
+            rec = {k: np.zeros(T, np.int32) for k in ("off_a", "off_b", "fill_buy", "fill_sell", "inventory")}
+            rec.update({k: np.zeros(T, np.float64) for k in ("cash", "reward", "pnl_reward", "fee_paid")})
+            for t in range(T):
+                raw_offsets = policy.get_action(env.inventory)
+                mid_p = (ask[t] + bid[t]) / 2.0
+                if name.startswith("glft"):
+                    off_a = ((mid_p + raw_offsets[0]) - ask[t]) / 0.001
+                    off_b = (bid[t] - (mid_p - raw_offsets[1])) / 0.001
+                    action = np.round([off_a, off_b]).astype(int)
+                else:
+                    action = np.round(raw_offsets).astype(int)
+                reward, info = env.step(action, mid[t], ask[t], bid[t], b_max[t], s_min[t])
+                rec["off_a"][t], rec["off_b"][t] = action[0], action[1]
+                rec["fill_buy"][t], rec["fill_sell"][t] = info["fill_buy"], info["fill_sell"]
+                rec["inventory"][t], rec["cash"][t] = env.inventory, env.cash
+                rec["reward"][t], rec["pnl_reward"][t], rec["fee_paid"][t] = reward, info["pnl_reward"], info["fee_paid"]
+            for k, v in rec.items():
+                out[f"{name}.fee{fee}.{k}"] = v
+            print("benchmark", name, fee, "fills", int(rec["fill_buy"].sum() + rec["fill_sell"].sum()),
+                  "offsets", np.unique(rec["off_a"]), np.unique(rec["off_b"]))
+    np.savez_compressed(os.path.join(OUT, "ref_benchmarks.npz"), **out)
+
+
 def tanh_threshold():
     cur = np.float32(0.5493)
     ys = []
@@ -228,6 +268,7 @@ def tanh_threshold():
 
 
 if __name__ == "__main__":
+    benchmark_policies()
     backtests()
     checkpoints()
     tanh_threshold()

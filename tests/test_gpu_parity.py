@@ -408,3 +408,28 @@ def test_full_size_properties(sg, orc):
     assert np.array_equal(bits64(f4.cpu().numpy()[idx]), bits64(fo)) and np.array_equal(t4.cpu().numpy()[idx], to)
     # checksum of checksums is launch-geometry independent
     assert f4.sum().item() == f1.sum().item()
+
+
+# ----------------------------------------------------------------------------------------------
+# benchmark rules (FOIC / GLFT) through the device step core vs the imported reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["glft", "glft_wide", "foic", "foic_1_2"])
+@pytest.mark.parametrize("fee", [0.0, 0.0003])
+def test_benchmark_policies_closed_loop_vs_reference(sg, name, fee):
+    import os
+    from conftest import GOLDEN
+    from sgmm_b200.benchmarks import FOICPolicy, GLFTPolicy
+    ref = np.load(os.path.join(GOLDEN, "ref_benchmarks.npz"))
+    bundle = tuple(ref[f"bundle.{k}"] for k in ("s1", "s2", "mid_next", "best_ask", "best_bid", "buy_max", "sell_min"))
+    pol = {"glft": GLFTPolicy(gamma=0.0001, kappa=3000, A=0.1, sigma=0.0005),
+           "glft_wide": GLFTPolicy(gamma=0.01, kappa=1500, A=0.1, sigma=0.02),
+           "foic": FOICPolicy(0, 0), "foic_1_2": FOICPolicy(1, 2)}[name]
+    z = np.zeros(len(bundle[0]), np.float32)
+    bun = sg.Bundle(z, z, *bundle[2:], 0.001)
+    fit, trades, tr = sg.rollout_table(bun, pol.table(bundle, 0.001), phi=1e-4, fee_rate=fee)
+    key = f"{name}.fee{fee}"
+    for k in ("off_a", "off_b", "fill_buy", "fill_sell", "inventory"):
+        assert np.array_equal(tr[k], ref[f"{key}.{k}"]), k
+    for k in ("cash", "reward", "pnl_reward", "fee_paid"):
+        assert np.array_equal(bits64(tr[k]), bits64(ref[f"{key}.{k}"])), k
+    assert trades == int(((ref[f"{key}.fill_buy"] == 1) | (ref[f"{key}.fill_sell"] == 1)).sum())

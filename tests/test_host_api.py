@@ -215,3 +215,25 @@ def test_synthetic_bundle_shape_and_determinism():
     assert 0.002 < np.isnan(bmax).mean() < 0.03
     touch0 = np.nanmean(bmax >= ask)
     assert 0.9 < touch0 <= 1.0
+
+
+def test_benchmark_policy_tables_match_reference_actions():
+    """FOIC / GLFT offset tables (host closed form) against the imported reference's benchmark run
+    (tests/golden/ref_benchmarks.npz: Env/benchmarks.py driven by the loop of main.py:99-132)."""
+    from conftest import GOLDEN
+    from sgmm_b200.benchmarks import FOICPolicy, GLFTPolicy
+    ref = np.load(os.path.join(GOLDEN, "ref_benchmarks.npz"))
+    bundle = tuple(ref[f"bundle.{k}"] for k in ("s1", "s2", "mid_next", "best_ask", "best_bid", "buy_max", "sell_min"))
+    pols = {"glft": GLFTPolicy(gamma=0.0001, kappa=3000, A=0.1, sigma=0.0005),
+            "glft_wide": GLFTPolicy(gamma=0.01, kappa=1500, A=0.1, sigma=0.02),
+            "foic": FOICPolicy(0, 0), "foic_1_2": FOICPolicy(1, 2)}
+    for name, pol in pols.items():
+        tab = pol.table(bundle, 0.001)
+        assert tab.shape == (480, 5, 2) and tab.dtype == np.int32
+        inv_prev = np.concatenate([[0], ref[f"{name}.fee0.0.inventory"][:-1]])
+        t = np.arange(480)
+        assert np.array_equal(tab[t, inv_prev + 2, 0], ref[f"{name}.fee0.0.off_a"])
+        assert np.array_equal(tab[t, inv_prev + 2, 1], ref[f"{name}.fee0.0.off_b"])
+    assert np.array_equal(FOICPolicy(1, 2).get_action(-1), [1, 2])
+    a = GLFTPolicy(gamma=0.0001, kappa=3000, A=0.1, sigma=0.0005).get_action(1)
+    assert a[0] > a[1] and a.dtype == np.float64            # long inventory skews the quotes down
