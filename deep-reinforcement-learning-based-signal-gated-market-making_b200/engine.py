@@ -277,6 +277,15 @@ class DeviceGA:
     def generation(self, train: Bundle, val: Bundle):
         _lib.check(_lib.lib().sgmm_ga_generation(self._h, train.handle, val.handle, _stream(self.device)))
 
+    def capture(self, train: Bundle, val: Bundle):
+        """Capture one generation (ask + rollout + tell + validation rollout + select: 4 kernels, no
+        host round trip) into a CUDA graph; ``graph.replay()`` then advances the GA by one generation.
+        Call :meth:`generation` once before capturing (first launches configure the kernels)."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.generation(train, val)
+        return g
+
     def status(self):
         s = _lib.GaStatus()
         _lib.check(_lib.lib().sgmm_ga_status_host(self._h, C.byref(s), _stream(self.device)))

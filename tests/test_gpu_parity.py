@@ -433,3 +433,29 @@ def test_benchmark_policies_closed_loop_vs_reference(sg, name, fee):
     for k in ("cash", "reward", "pnl_reward", "fee_paid"):
         assert np.array_equal(bits64(tr[k]), bits64(ref[f"{key}.{k}"])), k
     assert trades == int(((ref[f"{key}.fill_buy"] == 1) | (ref[f"{key}.fill_sell"] == 1)).sum())
+
+
+def test_ga_generation_cuda_graph_replay_matches_eager(sg):
+    from sgmm_b200 import synthetic
+    from sgmm_b200.engine import DeviceGA
+    tb = synthetic.synthetic_bundle(1, first_day=110)
+    vb = synthetic.synthetic_bundle(1, first_day=111)
+    stats = synthetic.train_stats_of(tb)
+    train = sg.Bundle.from_arrays(tb, stats, 0.001)
+    val = sg.Bundle.from_arrays(vb, stats, 0.001)
+    master, _ = synthetic.policy_like_genomes(1, seed=41)
+    kw = dict(pop_size=37, sigma=0.05, phi=1e-4, fee_rate=0.0, use_arl=False, seed=5, max_generations=8, patience=2)
+    eager = DeviceGA(master, None, **kw)
+    for _ in range(6):
+        eager.generation(train, val)
+    graphed = DeviceGA(master, None, **kw)
+    graphed.generation(train, val)                     # generation 0 eagerly (configures the kernels)
+    torch.cuda.synchronize()
+    g = graphed.capture(train, val)                    # capture advances nothing (capture does not execute)
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    he, hg = eager.history(6), graphed.history(6)
+    for k in he:
+        assert np.array_equal(he[k].view(np.uint8), hg[k].view(np.uint8)), k
+    assert np.array_equal(eager.masters()[0], graphed.masters()[0])
