@@ -202,7 +202,7 @@ __device__ __forceinline__ GenomeSource make_source(const PopArgs& p, int64_t i,
 // the rollout kernel (H = 32)
 // ---------------------------------------------------------------------------------------------
 // compute warps per CTA (one more warp is the producer): bounded by the register file
-__host__ __device__ constexpr int max_compute_warps(int U) { return U == 4 ? 7 : (U == 2 ? 12 : MAX_WARPS); }
+__host__ __device__ constexpr int max_compute_warps(int U) { return U == 4 ? 7 : (U == 2 ? 15 : MAX_WARPS); }
 
 struct RingSmem {
     uint64_t full[RING_STAGES];

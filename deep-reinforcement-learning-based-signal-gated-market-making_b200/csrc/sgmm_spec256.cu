@@ -42,9 +42,9 @@ constexpr int TILE_BARS = 25;                 // 25 bars x 5 inventories = 125 r
 constexpr int KBLK = 64;                      // bf16 elements per 128-byte swizzle row
 constexpr int NKB = H / KBLK;                 // 4 k-blocks
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 4;
-constexpr int WARP_MMA = 8, WARP_WALK = 9;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;      // epilogue: 2 column halves x 4 TMEM lane quarters
+constexpr int WARP_MMA = 12, WARP_WALK = 13;
+constexpr int NUM_THREADS = 448;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int64_t G = (int64_t)H * H + 7 * H + 2;       // 67330
 
@@ -62,6 +62,7 @@ struct Smem {
     float w1x[H], w1y[H], w1i[H], b1[H], b2[H], w3a[H], w3b[H];
     float b3[4];
     TableEntry table[2][TILE_ROWS];
+    float2 part[2][TILE_ROWS];                 // layer-3 partial sums of the upper column half
     uint64_t a_full[NKB], a_empty[NKB], d_full[2], d_empty[2], t_full[2], t_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
         for (int i = 0; i < NKB; ++i) { mbar_init(&sm.a_full[i], NUM_PROD_WARPS); mbar_init(&sm.a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.d_full[i], 1); mbar_init(&sm.d_empty[i], NUM_EPI_WARPS);
-            mbar_init(&sm.t_full[i], NUM_EPI_WARPS); mbar_init(&sm.t_empty[i], 1);
+            mbar_init(&sm.t_full[i], 4); mbar_init(&sm.t_empty[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -221,9 +222,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
 
         if (warp < NUM_EPI_WARPS) {
             // =========================== EPILOGUE ==============================================
-            const int row = warp * 32 + lane;
+            const int half = warp >> 2, quarter = warp & 3;      // column half, TMEM lane quarter (= warp % 4)
+            const int row = quarter * 32 + lane;
             const int tl = row / 5, iv = row % 5;          // bar within the tile, inventory index (inv+2)
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            const int col0 = half * (H / 2);
             for (int64_t it = 0; it < ntiles; ++it) {
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
                 // bar data of this row's step: issued before the accumulator is even ready so that the
@@ -231,28 +234,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const int64_t t = it * TILE_BARS + tl;
                 const bool valid = (row < TILE_BARS * 5) && (t < T);
                 const int64_t tc_ = valid ? t : 0;
-                const int2 kth = T > 0 ? __ldg(reinterpret_cast<const int2*>(&a.sig[tc_].ka1)) : make_int2(0, 0);
-                const double2 ab = T > 0 ? __ldg(reinterpret_cast<const double2*>(&a.px[tc_].ask)) : make_double2(0., 0.);
-                const double mid = T > 0 ? __ldg(&a.px[tc_].mid_next) : 0.0;
+                int2 kth = make_int2(0, 0); double2 ab = make_double2(0., 0.); double mid = 0.0;
+                if (half == 0 && T > 0) {
+                    kth = __ldg(reinterpret_cast<const int2*>(&a.sig[tc_].ka1));
+                    ab = __ldg(reinterpret_cast<const double2*>(&a.px[tc_].ask));
+                    mid = __ldg(&a.px[tc_].mid_next);
+                }
 
                 mbar_wait(&sm.d_full[buf], use & 1u);
                 tc_fence_after();
                 float2 accA[4], accB[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { accA[q] = make_float2(0.f, 0.f); accB[q] = make_float2(0.f, 0.f); }
-                const uint32_t tbase = lane_addr + buf * 256u;
+                const uint32_t tbase = lane_addr + buf * 256u + (uint32_t)col0;
                 uint32_t v[2][32];
                 tmem_ld32(tbase, v[0]);
 #pragma unroll
-                for (int cc = 0; cc < H / 32; ++cc) {
+                for (int cc = 0; cc < H / 64; ++cc) {
                     tmem_ld_wait();                                        // chunk cc has landed
-                    if (cc + 1 < H / 32) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
+                    if (cc + 1 < H / 64) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
                     const uint32_t* w = v[cc & 1];
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cc * 32 + c]);
-                        const float4 wa = *reinterpret_cast<const float4*>(&sm.w3a[cc * 32 + c]);
-                        const float4 wb = *reinterpret_cast<const float4*>(&sm.w3b[cc * 32 + c]);
+                        const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[col0 + cc * 32 + c]);
+                        const float4 wa = *reinterpret_cast<const float4*>(&sm.w3a[col0 + cc * 32 + c]);
+                        const float4 wb = *reinterpret_cast<const float4*>(&sm.w3b[col0 + cc * 32 + c]);
                         float2 x0 = __fadd2_rn(make_float2(__uint_as_float(w[c]), __uint_as_float(w[c + 1])), make_float2(bb.x, bb.y));
                         float2 x1 = __fadd2_rn(make_float2(__uint_as_float(w[c + 2]), __uint_as_float(w[c + 3])), make_float2(bb.z, bb.w));
                         x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f);
@@ -270,8 +276,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.d_empty[buf]);
 
-                const float ra = __fadd_rn(__fadd_rn(__fadd_rn(accA[0].x, accA[1].x), __fadd_rn(accA[0].y, accA[1].y)), sm.b3[0]);
-                const float rb = __fadd_rn(__fadd_rn(__fadd_rn(accB[0].x, accB[1].x), __fadd_rn(accB[0].y, accB[1].y)), sm.b3[1]);
+                // combine the two column halves: the upper half hands its partial sums over
+                float pa = __fadd_rn(__fadd_rn(accA[0].x, accA[1].x), __fadd_rn(accA[0].y, accA[1].y));
+                float pb = __fadd_rn(__fadd_rn(accB[0].x, accB[1].x), __fadd_rn(accB[0].y, accB[1].y));
+                if (half == 1) sm.part[g & 1u][row] = make_float2(pa, pb);
+                asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+                if (half == 1) continue;
+                const float2 other = sm.part[g & 1u][row];
+                const float ra = __fadd_rn(__fadd_rn(pa, other.x), sm.b3[0]);
+                const float rb = __fadd_rn(__fadd_rn(pb, other.y), sm.b3[1]);
                 const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));          // drl_engine.py:39
                 const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
                 // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
