@@ -111,6 +111,7 @@ int sgmm_bundle_create(sgmm_bundle** out, int64_t T, const float* z1, const floa
         if (!rc) rc = check_cuda(cudaMalloc(&b->px, n * sizeof(BarPx)), "cudaMalloc(px)");
         if (!rc) rc = check_cuda(cudaMalloc(&b->bmax, n * sizeof(double)), "cudaMalloc(buy_max)");
         if (!rc) rc = check_cuda(cudaMalloc(&b->smin, n * sizeof(double)), "cudaMalloc(sell_min)");
+        if (!rc) rc = check_cuda(cudaMalloc(&b->a1, tc32_a1_bytes(T)), "cudaMalloc(a1 tiles)");
         if (!rc) rc = check_cuda(cudaMalloc(&dz, 2 * n * sizeof(float)), "cudaMalloc(z staging)");
         if (!rc) rc = check_cuda(cudaMalloc(&dd, 3 * n * sizeof(double)), "cudaMalloc(price staging)");
         if (!rc) rc = check_cuda(cudaMemcpyAsync(dz, z1, n * sizeof(float), cudaMemcpyHostToDevice, st), "H2D z1");
@@ -121,6 +122,7 @@ int sgmm_bundle_create(sgmm_bundle** out, int64_t T, const float* z1, const floa
         if (!rc) rc = check_cuda(cudaMemcpyAsync(b->bmax, buy_max, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D buy_max");
         if (!rc) rc = check_cuda(cudaMemcpyAsync(b->smin, sell_min, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D sell_min");
         if (!rc) rc = launch_prologue(b, dz, dz + n, dd, dd + n, dd + 2 * n, st);
+        if (!rc) rc = launch_tc32_prologue(b, st);
         if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "bundle prologue");
         cudaFree(dz); cudaFree(dd);
     }
@@ -165,7 +167,7 @@ int sgmm_bundle_destroy(sgmm_bundle* b)
     if (!b) return SGMM_OK;
     {
         DeviceGuard guard(b->device);
-        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->ws);
+        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->a1); cudaFree(b->ws);
     }
     delete b;
     return SGMM_OK;
@@ -180,7 +182,9 @@ static int check_rollout_args(const sgmm_bundle* bundle, const sgmm_population* 
     if (mm->hidden == 256) {
         if (params->precision != SGMM_PRECISION_BF16) { set_error("hidden=256 runs on the tensor cores: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 path is built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
         if (adv) { set_error("the H=256 tensor-core rollout has no adversary path"); return SGMM_ERR_UNSUPPORTED; }
-    } else if (params->precision != SGMM_PRECISION_F32) { set_error("precision=SGMM_PRECISION_BF16 needs hidden=256"); return SGMM_ERR_UNSUPPORTED; }
+    } else if (mm->hidden == 32) {
+        if (params->precision == SGMM_PRECISION_BF16 && adv) { set_error("the H=32 tensor-core rollout (precision=SGMM_PRECISION_BF16) has no adversary path; use SGMM_PRECISION_F32"); return SGMM_ERR_UNSUPPORTED; }
+    } else if (params->precision != SGMM_PRECISION_F32) { set_error("precision=SGMM_PRECISION_BF16 needs hidden=32 or hidden=256"); return SGMM_ERR_UNSUPPORTED; }
     if (adv && adv->count != mm->count) { set_error("adv.count (%lld) != mm.count (%lld): MM i meets adversary i (Env/drl_engine.py:115)", (long long)adv->count, (long long)mm->count); return SGMM_ERR_INVALID; }
     if (adv && adv->hidden != 32) { set_error("adversary genomes are 1250-float TradingPolicy(32) genomes (models/model.py:63)"); return SGMM_ERR_INVALID; }
     return SGMM_OK;
@@ -196,6 +200,8 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
     DeviceGuard guard(bundle->device);
     if (mm->hidden == 256)
         return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
+    if (params->precision == SGMM_PRECISION_BF16)
+        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
     return launch_rollout(bundle, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                           params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
 }
@@ -204,10 +210,12 @@ int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population*
                                double* fitness, int32_t* trades, float* raw_table, int32_t* act_trace, void* stream)
 {
     if (int rc = check_rollout_args(bundle, mm, nullptr, params, fitness, trades)) return rc;
-    if (mm->hidden != 256) { set_error("audit entry is for hidden=256"); return SGMM_ERR_INVALID; }
+    if (params->precision != SGMM_PRECISION_BF16) { set_error("audit entry is for the tensor-core paths (precision=SGMM_PRECISION_BF16)"); return SGMM_ERR_INVALID; }
     PopArgs pm;
     if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
     DeviceGuard guard(bundle->device);
+    if (mm->hidden == 32)
+        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
     return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
 }
 
@@ -242,6 +250,8 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
     }
     if (mm->hidden == 256) {
         if (int rc = launch_spec256(b, pm, params->phi, params->fee_rate, d_fit, d_trd, nullptr, nullptr, st)) return rc;
+    } else if (params->precision == SGMM_PRECISION_BF16) {
+        if (int rc = launch_tc32(b, pm, params->phi, params->fee_rate, params->units_per_lane, d_fit, d_trd, nullptr, nullptr, st)) return rc;
     } else if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                                        params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
     if (int rc = check_cuda(cudaMemcpyAsync(fitness, d_fit, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H fitness")) return rc;

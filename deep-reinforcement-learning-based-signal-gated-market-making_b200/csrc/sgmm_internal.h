@@ -36,6 +36,7 @@ struct sgmm_bundle {
     sgmm::BarPx* px = nullptr;         // [T]
     double* bmax = nullptr;            // [T] raw bounds (trace kernel runs the literal step core)
     double* smin = nullptr;
+    uint8_t* a1 = nullptr;             // [ceil(T/25)][4096] layer-1 A operand tiles of the tensor-core H=32 path (sgmm_tc32.cu)
     // grow-only workspace of the *_host entry points
     std::mutex ws_mutex;
     void* ws = nullptr;
@@ -79,6 +80,10 @@ int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const
                  double* fitness, int32_t* trades, cudaStream_t st);
 int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades,
                    float* raw_table, int32_t* act_trace, cudaStream_t st);
+int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
+                float* raw_table, int32_t* act_trace, cudaStream_t st);
+int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st);
+size_t tc32_a1_bytes(int64_t T);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,
                     const double* ask, const double* bid, cudaStream_t st);
 

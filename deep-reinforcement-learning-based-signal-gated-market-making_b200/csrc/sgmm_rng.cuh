@@ -5,6 +5,7 @@
 //     noise(seed, generation, individual, element e) = normal4(key=seed, ctr=(e/4, ind_lo, ind_hi, gen))[e%4]
 #pragma once
 #include <stdint.h>
+#include "sgmm_internal.h"
 
 namespace sgmm {
 
@@ -109,5 +110,25 @@ struct GenomeSource {
         for (int i = 0; i < 4; ++i) v[i] = __fadd_rn(__ldg(row + e0 + i), __fmul_rn(n[i], sigma));
     }
 };
+
+// device scalars of the GA (best child index, decayed sigma, generation) override the host values
+__device__ __forceinline__ PopArgs resolve(const PopArgs& p)
+{
+    PopArgs r = p;
+    if (p.first_index_dev) r.first_index += *p.first_index_dev;
+    if (p.sigma_dev) r.sigma = *p.sigma_dev;
+    if (p.generation_dev) r.generation = (uint64_t)(*p.generation_dev);
+    return r;
+}
+
+__device__ __forceinline__ GenomeSource make_source(const PopArgs& p, int64_t i, int64_t G)
+{
+    GenomeSource g;
+    g.seeded = (p.genomes == nullptr);
+    g.row = g.seeded ? p.master : p.genomes + i * G;
+    g.sigma = p.sigma; g.seed = p.seed; g.generation = p.generation;
+    g.individual = (uint64_t)(p.first_index + i);
+    return g;
+}
 
 }  // namespace sgmm

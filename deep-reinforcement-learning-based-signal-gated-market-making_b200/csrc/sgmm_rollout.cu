@@ -179,25 +179,6 @@ __device__ __forceinline__ uint32_t table_lookup(uint32_t t0, uint32_t t1, uint3
     return (w >> ((s & 7) * 4)) & 15u;
 }
 
-__device__ __forceinline__ PopArgs resolve(const PopArgs& p)
-{
-    PopArgs r = p;
-    if (p.first_index_dev) r.first_index += *p.first_index_dev;
-    if (p.sigma_dev) r.sigma = *p.sigma_dev;
-    if (p.generation_dev) r.generation = (uint64_t)(*p.generation_dev);
-    return r;
-}
-
-__device__ __forceinline__ GenomeSource make_source(const PopArgs& p, int64_t i, int64_t G)
-{
-    GenomeSource g;
-    g.seeded = (p.genomes == nullptr);
-    g.row = g.seeded ? p.master : p.genomes + i * G;
-    g.sigma = p.sigma; g.seed = p.seed; g.generation = p.generation;
-    g.individual = (uint64_t)(p.first_index + i);
-    return g;
-}
-
 // ---------------------------------------------------------------------------------------------
 // the rollout kernel (H = 32)
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,666 @@
+// sgmm_tc32.cu -- H = 32 population rollout with ALL THREE policy layers on the tcgen05 tensor cores.
+//
+// The sequential rollout (Env/drl_engine.py:31-61) is a chain of per-individual 32x32 GEMVs.  The
+// inventory is a 5-valued integer (Env/market_env.py:14-15,34-35), so the action at bar t depends on
+// (t, inv) only: evaluate the policy for ALL five inventories of every bar and each
+// layer becomes a GEMM whose M dimension is (bar, inventory):
+//     tile = 25 bars x 5 inventories = 125 rows (+3 idle) = one M=128 tcgen05.mma
+//     L1  D1[128,32] = A1[128,16] * B1^T      A1 = bf16 split of [z1, z2, inv/2, 1] (shared by the WHOLE
+//                                             population: precomputed once per bundle, TMA'd to smem)
+//                                             B1 = matching bf16 split of W1 | b1 (fp32-grade layer 1)
+//     L2  D2[128,32] = A2[128,48] * B2^T      A2 = relu(D1) as bf16 IN TENSOR MEMORY (tcgen05.st; the MMA
+//                                             reads its A operand from TMEM) | 1 | 1;  B2 = W2 | b2 hi | b2 lo
+//     L3  D3[128,16] = A3[128,48] * B3^T      A3 = relu(D2) bf16 in TMEM | 1 | 1;  B3 rows 0,1 = W3 | b3 (hi),
+//                                             rows 2,3 = bf16 residual of W3 | b3 (lo), rest 0
+// so the CUDA cores never touch a weight: per row they only do TMEM -> cvt.rn.relu.bf16x2 -> TMEM twice,
+// then quantise (x5, round-half-even, drl_engine.py:39) and take the SPECULATIVE env step of the row's
+// (bar, inventory) (market_env.py:30-58) -> (fp64 reward, next inventory).  A walker lane per individual
+// then follows the 5-state automaton through the table (reference order fp64 reward sum).
+//
+// One persistent CTA per SM works on a GROUP of up to 16 individuals in lockstep over time: the A1 tile
+// of a 25-bar chunk is loaded once and multiplied with every individual's weights (a grouped GEMM:
+// per-individual B operands, shared A operand), 16 walker lanes advance 16 independent automata.
+//   warps 0-7   E1 : D1 -> relu -> bf16 -> A2   (warp % 4 = TMEM lane quarter; warps 0-3 own TMEM buffer 0 =
+//   warps 8-15  E2 : D2 -> relu -> bf16 -> A3    even tiles, warps 4-7 buffer 1 = odd tiles, likewise below)
+//   warps 16-23 E3 : D3 -> offsets -> speculative env step -> table
+//   warps 24-26 L1 / L2 / L3 issuers: a converged warp each, one elected lane issues tcgen05.mma + commit
+//               (three independent issue streams; the L1 warp also feeds the A1 ring with TMA bulk copies)
+//   warp  27    walker
+// Every TMEM region is double-buffered; per layer and buffer one "ready" mbarrier (A written + D drained)
+// and one "done" mbarrier (tcgen05.commit).
+//
+// Precision: A2/A3/W2/W3 are bf16 (fp32 accumulate); layer 1 and all biases carry a hi+lo bf16 split.
+// tests/test_gpu_tc32.py states the tolerance against the fp32 oracle and checks that GIVEN the offsets
+// the kernel took, fills / inventory / trades / rewards / fitness are bit-identical to the oracle.
+#include <cuda_bf16.h>
+#include "sgmm_internal.h"
+#include "sgmm_rng.cuh"
+#include "sgmm_step_core.h"
+
+namespace sgmm {
+
+namespace tc32 {
+
+constexpr int H = 32;
+constexpr int TILE_ROWS = 128;
+constexpr int TILE_BARS = 25;
+constexpr int GMAX = 16;                       // individuals per CTA group (even: tiles travel in pairs)
+constexpr int K1 = 16, K2 = 48;
+constexpr int A1_BYTES = TILE_ROWS * K1 * 2;   // 4096
+constexpr int B1_BYTES = H * K1 * 2;           // 1024
+constexpr int B2_BYTES = H * K2 * 2;           // 3072
+constexpr int B3_BYTES = 16 * K2 * 2;          // 1536
+constexpr int A1_STAGES = 4;
+constexpr int WARP_L1 = 24, WARP_L2 = 25, WARP_L3 = 26;     // warp 27 = walker
+constexpr int NUM_THREADS = 896;
+constexpr uint32_t TMEM_COLS = 512;
+// TMEM column map.  The pipeline moves UNITS of two tiles (the same 25-bar chunk for two individuals of the
+// group), so that every mbarrier round trip and every issuer iteration is shared by two tiles.  Two unit
+// buffers of 256 columns each; inside a buffer tile j of the unit sits at + j * S_*:
+constexpr uint32_t BUF_COLS = 256;
+constexpr uint32_t C_D1 = 0, C_A2 = 64, C_D2 = 112, C_A3 = 176, C_D3 = 224;
+constexpr uint32_t S_D = 32, S_A = 24, S_D3 = 16;
+constexpr int64_t G32 = 1250;
+constexpr int TAB_R_STRIDE = TILE_ROWS + 1;    // doubles per individual: 258 words -> walker lanes hit distinct banks
+constexpr int TAB_N_STRIDE = TILE_BARS * 8;    // bytes per individual: 50 words -> distinct bank pairs
+
+struct Smem {
+    uint8_t a1[A1_STAGES][A1_BYTES];
+    uint8_t b1[GMAX][B1_BYTES];
+    uint8_t b2[GMAX][B2_BYTES];
+    uint8_t b3[GMAX][B3_BYTES];
+    double tab_r[2][GMAX][TAB_R_STRIDE];       // reward of (bar, inventory) rows
+    uint8_t tab_n[2][GMAX][TAB_N_STRIDE];      // next inventory index | traded << 3, 8 bytes per bar
+    uint64_t a1_full[A1_STAGES], a1_empty[A1_STAGES];
+    // per layer and TMEM buffer: ready = inputs of the MMA are in place (A written, previous D drained),
+    // done = tcgen05.commit of the layer's MMAs (D complete AND the A buffer it read is free again)
+    uint64_t l1_ready[2], l1_done[2], l2_ready[2], l2_done[2], l3_ready[2], l3_done[2];
+    uint64_t tab_full[2], tab_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "LAB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 = distance between the two 16-byte k-chunks of one K=16 step
+//   | [32,46) SBO>>4 = distance between 8-row groups | [46,48) version = 1 | [61,64) layout = 0
+// (checked on the device by tools/tc32_unit.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// canonical offset of element (r, k) of a [rows][K] bf16 K-major tile: 8 x 16-byte core matrices,
+// k-chunks 128 B apart, 8-row groups (K/8)*128 B apart
+__host__ __device__ __forceinline__ uint32_t canon(int r, int k, int K) { return (uint32_t)(((r >> 3) * (K >> 3) + (k >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2); }
+
+// instruction descriptor: c = f32 (bit 4), a = b = bf16 (bits 7, 10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t idesc(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24); }
+
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d), "l"(ad), "l"(bd), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t id, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "l"(bd), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// two fp32 -> packed bf16x2 with ReLU; `lo` lands in the low half (even k)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// x = hi + mid + lo with each piece exactly representable in bf16
+__device__ __forceinline__ void split3(float x, float& hi, float& mid, float& lo)
+{
+    hi = bf16_round(x);
+    const float r1 = __fadd_rn(x, -hi);
+    mid = bf16_round(r1);
+    lo = bf16_round(__fadd_rn(r1, -mid));
+}
+
+struct Args {
+    const BarSig* sig; const BarPx* px; const uint8_t* a1; int64_t T;
+    double tick, phi, fee;
+    PopArgs mm;
+    int32_t group;           // individuals per CTA group (<= GMAX)
+    double* fitness; int32_t* trades;
+    float* raw_table;        // optional audit output [P][T][5][2]
+    int32_t* act_trace;      // optional audit output [P][T][2] : actions actually taken
+};
+
+// ---------------------------------------------------------------------------------------------
+// bundle prologue: the layer-1 A operand of every 25-bar chunk, in the canonical K-major layout
+//   k: 0 z1h 1 z1m 2 z1l 3 z1h 4 z1m 5 z1h | 6 z2h 7 z2m 8 z2l 9 z2h 10 z2m 11 z2h | 12 inv/2 13 inv/2 | 14 1 15 1
+// against B1 (stage_weights): w0h w0h w0h w0m w0m w0l | w1h w1h w1h w1m w1m w1l | w2h w2m | b1h b1m
+// ---------------------------------------------------------------------------------------------
+__global__ void tc32_a1_kernel(int64_t T, int64_t nchunks, const BarSig* __restrict__ sig, uint8_t* __restrict__ a1)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nchunks * TILE_ROWS) return;
+    const int64_t c = idx / TILE_ROWS;
+    const int r = (int)(idx % TILE_ROWS);
+    const int64_t t = c * TILE_BARS + r / 5;
+    uint16_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0;
+    if (r < TILE_BARS * 5 && t < T) {
+        const float z1 = sig[t].z1, z2 = sig[t].z2;
+        float h, m, l;
+        split3(z1, h, m, l);
+        v[0] = v[3] = v[5] = bf16_bits(h); v[1] = v[4] = bf16_bits(m); v[2] = bf16_bits(l);
+        split3(z2, h, m, l);
+        v[6] = v[9] = v[11] = bf16_bits(h); v[7] = v[10] = bf16_bits(m); v[8] = bf16_bits(l);
+        v[12] = v[13] = bf16_bits((float)(r % 5 - 2) * 0.5f);            // drl_engine.py:35
+        v[14] = v[15] = bf16_bits(1.0f);
+    }
+    uint8_t* tile = a1 + c * A1_BYTES;
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+        uint4 o;
+        o.x = v[kc * 8 + 0] | ((uint32_t)v[kc * 8 + 1] << 16); o.y = v[kc * 8 + 2] | ((uint32_t)v[kc * 8 + 3] << 16);
+        o.z = v[kc * 8 + 4] | ((uint32_t)v[kc * 8 + 5] << 16); o.w = v[kc * 8 + 6] | ((uint32_t)v[kc * 8 + 7] << 16);
+        *reinterpret_cast<uint4*>(tile + canon(r, kc * 8, K1)) = o;
+    }
+}
+
+// one genome element -> its bf16 slots in the B operands of individual slot g
+__device__ __forceinline__ void scatter_weight(Smem& sm, int g, int e, float v)
+{
+    auto put = [](uint8_t* base, uint32_t off, float x) { *reinterpret_cast<uint16_t*>(base + off) = bf16_bits(x); };
+    if (e < 96) {                                      // W1[j, i]   (models/model.py:10)
+        const int j = e / 3, i = e % 3;
+        float h, m, l; split3(v, h, m, l);
+        uint8_t* b = sm.b1[g];
+        if (i < 2) {
+            const int k0 = i * 6;
+            put(b, canon(j, k0 + 0, K1), h); put(b, canon(j, k0 + 1, K1), h); put(b, canon(j, k0 + 2, K1), h);
+            put(b, canon(j, k0 + 3, K1), m); put(b, canon(j, k0 + 4, K1), m); put(b, canon(j, k0 + 5, K1), l);
+        } else {
+            put(b, canon(j, 12, K1), h); put(b, canon(j, 13, K1), m);
+        }
+    } else if (e < 128) {                              // b1[j]
+        const int j = e - 96;
+        const float h = bf16_round(v), m = bf16_round(__fadd_rn(v, -h));
+        put(sm.b1[g], canon(j, 14, K1), h); put(sm.b1[g], canon(j, 15, K1), m);
+    } else if (e < 1152) {                             // W2[j, k]
+        const int j = (e - 128) >> 5, k = (e - 128) & 31;
+        put(sm.b2[g], canon(j, k, K2), v);
+    } else if (e < 1184) {                             // b2[j] -> K slots 32 (hi), 33 (lo), multiplied by the constant 1 columns of A2
+        const int j = e - 1152;
+        const float h = bf16_round(v), m = bf16_round(__fadd_rn(v, -h));
+        put(sm.b2[g], canon(j, 32, K2), h); put(sm.b2[g], canon(j, 33, K2), m);
+    } else if (e < 1248) {                             // W3[o, k]: row o = hi, row o+2 = bf16 residual
+        const int o = (e - 1184) >> 5, k = (e - 1184) & 31;
+        const float h = bf16_round(v), m = bf16_round(__fadd_rn(v, -h));
+        put(sm.b3[g], canon(o, k, K2), h); put(sm.b3[g], canon(o + 2, k, K2), m);
+    } else {                                           // b3[o]
+        const int o = e - 1248;
+        const float h = bf16_round(v), m = bf16_round(__fadd_rn(v, -h));
+        put(sm.b3[g], canon(o, 32, K2), h); put(sm.b3[g], canon(o, 33, K2), m);
+    }
+}
+
+// one lane of a converged warp (the tcgen05 issue pattern: the branch is warp-uniform for the compiler)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+template <bool FEE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t misalign = smem_u32(smem_raw) & 127u;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - misalign) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t T = a.T;
+    const int G = a.group;
+    const uint32_t nchunks = (uint32_t)((T + TILE_BARS - 1) / TILE_BARS);
+    const uint32_t UG = (uint32_t)G >> 1;                       // units (pairs of individuals) per chunk
+    const uint32_t nunits = nchunks * UG;
+
+    if (tid == 0) {
+        for (int i = 0; i < A1_STAGES; ++i) { mbar_init(&sm.a1_full[i], 1); mbar_init(&sm.a1_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.l1_ready[i], 4); mbar_init(&sm.l1_done[i], 1);
+            mbar_init(&sm.l2_ready[i], 8); mbar_init(&sm.l2_done[i], 1);
+            mbar_init(&sm.l3_ready[i], 8); mbar_init(&sm.l3_done[i], 1);
+            mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WARP_L1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // B operands: the padding (K slots 34..47, B3 rows 4..15) stays zero for the whole kernel
+    for (int i = tid; i < GMAX * (B1_BYTES + B2_BYTES + B3_BYTES) / 16; i += NUM_THREADS)
+        reinterpret_cast<uint4*>(&sm.b1[0][0])[i] = make_uint4(0, 0, 0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may touch (warp % 4)
+    const uint32_t pset = (uint32_t)(warp >> 2) & 1u;     // epilogue warps: which of the two TMEM buffers (tile parity) is theirs
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    if (warp < 16) {
+        // constant tail of the A2 / A3 operands: K slots 32, 33 = 1.0 (bias rows of B2 / B3), 34..47 = 0
+        const uint32_t cbase = (warp < 8 ? C_A2 : C_A3) + pset * BUF_COLS;
+        uint32_t c[8] = {0x3F803F80u, 0, 0, 0, 0, 0, 0, 0};
+        tmem_st8(lane_addr + cbase + 16, c);
+        tmem_st8(lane_addr + cbase + S_A + 16, c);
+        tmem_st_wait();
+    }
+    // "accumulator drained" half of the first use of the l2 / l3 ready barriers
+    if (warp >= 8 && warp < 16 && lane == 0) mbar_arrive(&sm.l2_ready[pset]);
+    if (warp >= 16 && warp < 24 && lane == 0) mbar_arrive(&sm.l3_ready[pset]);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const PopArgs pop = resolve(a.mm);
+    uint32_t gt = 0;                               // units processed so far by this CTA (pipeline phase source)
+    uint32_t gc = 0;                               // chunks processed so far
+
+    for (int64_t grp = blockIdx.x; grp * G < pop.count; grp += gridDim.x) {
+        // ---------------- stage the group's weights (all warps) ----------------------------------
+        for (int task = tid; task < G * 313; task += NUM_THREADS) {
+            const int g = task / 313, q = task % 313;
+            const int64_t ind = grp * G + g;
+            const bool live = ind < pop.count;
+            const GenomeSource src = make_source(pop, live ? ind : 0, G32);
+            const int e0 = q * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (live) {
+                if (q < 312) src.at4(e0, v);
+                else { v[0] = src.at(e0); v[1] = src.at(e0 + 1); }
+            }
+            if (e0 >= 128 && e0 < 1152) {                       // 4 consecutive k of one W2 row: one 8-byte store
+                const int j = (e0 - 128) >> 5, k = (e0 - 128) & 31;
+                uint2 o;
+                o.x = bf16_bits(v[0]) | ((uint32_t)bf16_bits(v[1]) << 16);
+                o.y = bf16_bits(v[2]) | ((uint32_t)bf16_bits(v[3]) << 16);
+                *reinterpret_cast<uint2*>(sm.b2[g] + canon(j, k, K2)) = o;
+            } else {
+                const int n = q < 312 ? 4 : 2;
+                for (int i = 0; i < n; ++i) scatter_weight(sm, g, e0 + i, v[i]);
+            }
+        }
+        fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+
+        // first unit of this group that lands in this warp's TMEM buffer
+        const uint32_t it0 = ((gt & 1u) == pset) ? 0u : 1u;
+
+        if (warp < 16) {
+            // =========================== E1 / E2 : D -> relu -> bf16 -> next A ====================
+            const bool first = warp < 8;
+            uint64_t* done_in = first ? &sm.l1_done[pset] : &sm.l2_done[pset];       // accumulator complete
+            uint64_t* drained = first ? &sm.l1_ready[pset] : &sm.l2_ready[pset];     // accumulator read out
+            uint64_t* done_out = first ? &sm.l2_done[pset] : &sm.l3_done[pset];      // MMAs that read the A buffer retired
+            uint64_t* filled = first ? &sm.l2_ready[pset] : &sm.l3_ready[pset];      // A buffer written
+            const uint32_t d_addr = lane_addr + (first ? C_D1 : C_D2) + pset * BUF_COLS;
+            const uint32_t a_addr = lane_addr + (first ? C_A2 : C_A3) + pset * BUF_COLS;
+#pragma unroll 1
+            for (uint32_t it = it0; it < nunits; it += 2) {
+                const uint32_t par = ((gt + it) >> 1) & 1u;
+                mbar_wait(done_in, par);
+                tc_fence_after();
+                uint32_t v[32], p[16];
+                tmem_ld32(d_addr, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                tmem_ld32(d_addr + S_D, v);                                  // second tile of the unit
+                mbar_wait(done_out, par ^ 1u);                               // the MMAs that read this A buffer have retired
+                tc_fence_after();
+                tmem_st16(a_addr, p);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(drained);                         // accumulator read out
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                tmem_st16(a_addr + S_A, p);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(filled);
+            }
+        } else if (warp < 24) {
+            // =========================== E3 : offsets, speculative env step, table ================
+            const int row = quarter * 32 + lane;
+            const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
+            const bool row_ok = row < TILE_BARS * 5;
+            const uint32_t d_addr = lane_addr + C_D3 + pset * BUF_COLS;
+            int2 kth = make_int2(0, 0), kth_n = make_int2(0, 0);
+            double2 ab = make_double2(0., 0.), ab_n = make_double2(0., 0.);
+            double mid = 0.0, mid_n = 0.0;
+            auto load_bar = [&](uint32_t c, int2& k, double2& q, double& m) {
+                const int64_t t = (int64_t)c * TILE_BARS + tl;
+                if (row_ok && t < T) {
+                    k = __ldg(reinterpret_cast<const int2*>(&a.sig[t].ka1));
+                    q = __ldg(reinterpret_cast<const double2*>(&a.px[t].ask));
+                    m = __ldg(&a.px[t].mid_next);
+                }
+            };
+            uint32_t c_cur = 0xFFFFFFFFu;
+            if (it0 < nunits) load_bar(it0 / UG, kth_n, ab_n, mid_n);
+#pragma unroll 1
+            for (uint32_t it = it0; it < nunits; it += 2) {
+                const uint32_t par = ((gt + it) >> 1) & 1u;
+                const uint32_t c = it / UG;
+                const int g0 = (int)(it - c * UG) * 2;
+                const uint32_t q = gc + c, cbuf = q & 1u, cpar = (q >> 1) & 1u;
+                const int64_t t = (int64_t)c * TILE_BARS + tl;
+                const bool valid = row_ok && t < T;
+                if (c != c_cur) {                                                     // this warp's first unit of chunk c
+                    c_cur = c;
+                    kth = kth_n; ab = ab_n; mid = mid_n;
+                    const uint32_t cn = c + (UG == 1 ? 2u : 1u);                      // the next chunk this warp will see
+                    if (cn < nchunks) load_bar(cn, kth_n, ab_n, mid_n);               // prefetch its bars
+                    mbar_wait(&sm.tab_empty[cbuf], cpar ^ 1u);                        // walker has left this table buffer
+                }
+                mbar_wait(&sm.l3_done[pset], par);
+                tc_fence_after();
+                uint32_t v[2][4];
+                tmem_ld4(d_addr, v[0]);
+                tmem_ld4(d_addr + S_D3, v[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.l3_ready[pset]);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int g = g0 + j;
+                    const float ra = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));      // hi + lo halves of W3
+                    const float rb = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
+                    const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));                            // drl_engine.py:39
+                    const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
+                    if (valid) {
+                        // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
+                        const int inv = iv - 2;
+                        const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
+                        const bool fs = (inv > -2) && (ka < kth.x);              // :35,:38
+                        const double my_ask = add_rn(ab.x, mul_rn((double)ka, a.tick));
+                        const double my_bid = sub_rn(ab.y, mul_rn((double)kb, a.tick));
+                        double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
+                        if (FEE) {
+                            leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
+                            leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
+                        }
+                        double pnl = 0.0;
+                        pnl = fb ? add_rn(pnl, leg_b) : pnl;
+                        pnl = fs ? add_rn(pnl, leg_s) : pnl;
+                        const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
+                        const int ai = ninv < 0 ? -ninv : ninv;
+                        sm.tab_r[cbuf][g][row] = sub_rn(pnl, mul_rn(a.phi, (double)ai));           // :57-58
+                        sm.tab_n[cbuf][g][tl * 8 + iv] = (uint8_t)((ninv + 2) | ((fb || fs) ? 8 : 0));
+                        if (a.raw_table) {
+                            const int64_t ind = grp * G + g;
+                            if (ind < pop.count) {
+                                float* o = a.raw_table + (((int64_t)ind * T + t) * 5 + iv) * 2;
+                                __stcg(o, ra); __stcg(o + 1, rb);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tab_full[cbuf]);
+            }
+        } else if (warp == WARP_L1) {
+            // =========================== L1 ISSUER + A1 TMA PRODUCER ===============================
+            // the whole warp runs the loop converged; one elected lane issues (same lane every time)
+            auto load_a1 = [&](uint32_t c) {
+                const uint32_t q = gc + c, slot = q % A1_STAGES, use = q / A1_STAGES;
+                mbar_wait(&sm.a1_empty[slot], (use & 1u) ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&sm.a1_full[slot], A1_BYTES);
+                    tma_bulk_g2s(sm.a1[slot], a.a1 + (size_t)c * A1_BYTES, A1_BYTES, &sm.a1_full[slot]);
+                }
+                __syncwarp();
+            };
+            for (uint32_t c = 0; c < nchunks && c < (uint32_t)(A1_STAGES - 1); ++c) load_a1(c);
+            constexpr uint32_t ID32 = idesc(32);
+            const uint64_t b1d0 = make_desc(smem_u32(sm.b1[0]), 128, 256);
+            uint32_t c1 = 0, u1 = 0;
+            uint64_t ad = 0;
+#pragma unroll 1
+            for (uint32_t it = 0; it < nunits; ++it) {
+                const uint32_t i = gt + it, buf = i & 1u, par = (i >> 1) & 1u;
+                const uint32_t q = gc + c1, slot = q % A1_STAGES, use = q / A1_STAGES;
+                if (u1 == 0) {
+                    if (c1 + A1_STAGES - 1 < nchunks) load_a1(c1 + A1_STAGES - 1);
+                    mbar_wait(&sm.a1_full[slot], use & 1u);
+                    ad = make_desc(smem_u32(sm.a1[slot]), 128, 256);
+                }
+                mbar_wait(&sm.l1_ready[buf], par ^ 1u);
+                tc_fence_after();
+                const bool last = (u1 + 1 == UG);
+                if (elect_one()) {
+                    const uint64_t bd = b1d0 + (uint64_t)(u1 * 2u * (uint32_t)(B1_BYTES >> 4));
+                    const uint32_t d = tmem_base + C_D1 + buf * BUF_COLS;
+                    umma_ss(d, ad, bd, ID32, 0u);
+                    umma_ss(d + S_D, ad, bd + (uint64_t)(B1_BYTES >> 4), ID32, 0u);
+                    umma_commit(&sm.l1_done[buf]);
+                    if (last) umma_commit(&sm.a1_empty[slot]);
+                }
+                __syncwarp();
+                if (last) { u1 = 0; ++c1; } else ++u1;
+            }
+        } else if (warp == WARP_L2 || warp == WARP_L3) {
+            // =========================== L2 / L3 ISSUER ============================================
+            const bool second = warp == WARP_L2;
+            uint64_t* ready = second ? sm.l2_ready : sm.l3_ready;
+            uint64_t* done = second ? sm.l2_done : sm.l3_done;
+            const uint32_t id = second ? idesc(32) : idesc(16);
+            const uint32_t d_col = tmem_base + (second ? C_D2 : C_D3), d_step = second ? S_D : S_D3;
+            const uint32_t a_col = tmem_base + (second ? C_A2 : C_A3);
+            const uint64_t bd0 = make_desc(second ? smem_u32(sm.b2[0]) : smem_u32(sm.b3[0]), 128, 768);
+            const uint32_t bstep = (uint32_t)((second ? B2_BYTES : B3_BYTES) >> 4);
+            uint32_t u = 0;
+#pragma unroll 1
+            for (uint32_t it = 0; it < nunits; ++it) {
+                const uint32_t i = gt + it, buf = i & 1u, par = (i >> 1) & 1u;
+                mbar_wait(&ready[buf], par);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t bd = bd0 + (uint64_t)(u * 2u * bstep);
+                    const uint32_t d = d_col + buf * BUF_COLS, aa = a_col + buf * BUF_COLS;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t bj = bd + (uint64_t)((uint32_t)j * bstep);
+                        const uint32_t dj = d + (uint32_t)j * d_step, aj = aa + (uint32_t)j * S_A;
+                        umma_ts(dj, aj, bj, id, 0u);
+                        umma_ts(dj, aj + 8, bj + 16, id, 1u);          // +256 B per K=16 step
+                        umma_ts(dj, aj + 16, bj + 32, id, 1u);
+                    }
+                    umma_commit(&done[buf]);
+                }
+                __syncwarp();
+                if (++u == UG) u = 0;
+            }
+        } else {
+            // =========================== WALKER : one lane per individual ==========================
+            const int g = lane;
+            const int64_t ind = grp * G + g;
+            const bool live = g < G && ind < pop.count;
+            int iv = 2, trades = 0;                                       // inventory 0
+            double total = 0.0;                                           // drl_engine.py:26
+#pragma unroll 1
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                const uint32_t q = gc + c, cbuf = q & 1u, cpar = (q >> 1) & 1u;
+                mbar_wait(&sm.tab_full[cbuf], cpar);
+                if (live) {
+                    const int64_t t0 = (int64_t)c * TILE_BARS;
+                    const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
+                    const uint8_t* nb = sm.tab_n[cbuf][g];
+                    const double* rb = sm.tab_r[cbuf][g];
+#pragma unroll
+                    for (int s = 0; s < TILE_BARS; ++s) {
+                        if (s < n) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(nb + s * 8);
+                            const uint32_t e = __byte_perm(w.x, w.y, (uint32_t)iv) & 0xFFu;
+                            total = add_rn(total, rb[s * 5 + iv]);                // drl_engine.py:54
+                            trades += (int)(e >> 3);                              // :60-61
+                            if (a.act_trace) {
+                                const float* o = a.raw_table + (((int64_t)ind * T + t0 + s) * 5 + iv) * 2;
+                                int32_t* at = a.act_trace + ((int64_t)ind * T + t0 + s) * 2;
+                                at[0] = __float2int_rn(__fmul_rn(__ldcg(o), 5.0f));
+                                at[1] = __float2int_rn(__fmul_rn(__ldcg(o + 1), 5.0f));
+                            }
+                            iv = (int)(e & 7u);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tab_empty[cbuf]);
+            }
+            if (live) {
+                if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
+                a.fitness[ind] = total; a.trades[ind] = trades;
+            }
+        }
+        gt += nunits;
+        gc += nchunks;
+        tc_fence_before();
+        __syncthreads();                            // every role is done with this group's weights and tables
+        tc_fence_after();
+    }
+
+    if (warp == WARP_L1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc32
+
+int tc32_chunks(int64_t T) { return (int)((T + tc32::TILE_BARS - 1) / tc32::TILE_BARS); }
+size_t tc32_a1_bytes(int64_t T) { return (size_t)tc32_chunks(T) * tc32::A1_BYTES; }
+
+int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st)
+{
+    using namespace tc32;
+    if (b->T == 0) return SGMM_OK;
+    const int64_t nchunks = tc32_chunks(b->T);
+    const int64_t n = nchunks * TILE_ROWS;
+    tc32_a1_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->T, nchunks, b->sig, b->a1);
+    return check_cuda(cudaGetLastError(), "tc32_a1_kernel launch");
+}
+
+// individuals per CTA group: minimise waves x group (the time of one launch), prefer the larger group
+int tc32_group_size(int64_t count, int sms)
+{
+    int best = 2; int64_t best_cost = INT64_MAX;
+    for (int g = 2; g <= tc32::GMAX; g += 2) {
+        const int64_t groups = (count + g - 1) / g;
+        const int64_t waves = (groups + sms - 1) / sms;
+        const int64_t cost = waves * g;
+        if (cost <= best_cost) { best_cost = cost; best = g; }
+    }
+    return best;
+}
+
+int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
+                float* raw_table, int32_t* act_trace, cudaStream_t st)
+{
+    using namespace tc32;
+    if (mm.count == 0) return SGMM_OK;
+    if (act_trace && !raw_table) { set_error("act_trace needs raw_table"); return SGMM_ERR_INVALID; }
+    Args a;
+    a.sig = b->sig; a.px = b->px; a.a1 = b->a1; a.T = b->T; a.tick = b->tick; a.phi = phi; a.fee = fee;
+    a.mm = mm; a.fitness = fitness; a.trades = trades; a.raw_table = raw_table; a.act_trace = act_trace;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+    a.group = (group >= 2 && group <= GMAX && group % 2 == 0) ? group : tc32_group_size(mm.count, sms);
+    const int64_t groups = (mm.count + a.group - 1) / a.group;
+    const int grid = (int)(groups < sms ? groups : sms);
+    const size_t smem = sizeof(Smem) + 128;
+    static bool configured[2] = {false, false};
+    const bool has_fee = fee != 0.0;
+    auto kern = has_fee ? tc32_kernel<true> : tc32_kernel<false>;
+    if (!configured[has_fee]) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                "cudaFuncSetAttribute(tc32 smem)")) return rc;
+        configured[has_fee] = true;
+    }
+    kern<<<grid, NUM_THREADS, smem, st>>>(a);
+    return check_cuda(cudaGetLastError(), "tc32_kernel launch");
+}
+
+}  // namespace sgmm

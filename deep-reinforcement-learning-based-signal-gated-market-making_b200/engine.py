@@ -32,9 +32,20 @@ def _stream(device):
 PRECISION_F32, PRECISION_BF16 = 0, 1
 
 
-def _params(phi, fee_rate, units_per_lane=0, warps_per_cta=0, hidden=32):
-    """hidden=32 -> bit-exact SGMM-F32 path; hidden=256 -> tcgen05 tensor-core path (bf16 inputs)."""
-    prec = PRECISION_BF16 if hidden == 256 else PRECISION_F32
+def _precision(precision, hidden):
+    """None -> the default of the width: hidden=32 bit-exact SGMM-F32 path, hidden=256 tcgen05 path.
+    "bf16" with hidden=32 selects the tensor-core rollout of sgmm_tc32.cu (all three layers on tcgen05)."""
+    if precision is None:
+        return PRECISION_BF16 if hidden == 256 else PRECISION_F32
+    if precision in ("f32", "fp32", PRECISION_F32):
+        return PRECISION_F32
+    if precision in ("bf16", "tensor", PRECISION_BF16):
+        return PRECISION_BF16
+    raise ValueError(f"unknown precision {precision!r}")
+
+
+def _params(phi, fee_rate, units_per_lane=0, warps_per_cta=0, hidden=32, precision=None):
+    prec = _precision(precision, hidden)
     return _lib.RolloutParams(float(phi), float(fee_rate), prec, 0, int(units_per_lane), int(warps_per_cta))
 
 
@@ -53,7 +64,7 @@ def _as_f32_matrix(x, width):
 
 
 def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_rate=0.0, hidden=32,
-                       units_per_lane=0, warps_per_cta=0):
+                       units_per_lane=0, warps_per_cta=0, precision=None):
     """One episode per individual (the reference's ``pool.starmap(evaluate_individual, ...)``).
 
     ``genomes``: [P, G] float32 -- CUDA tensor (device path, returns CUDA tensors, no sync) or
@@ -70,7 +81,7 @@ def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_ra
     L = _lib.lib()
     mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
     adv = None if a is None else _lib.Population(32, 0, P, a.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
-    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta, hidden)
+    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta, hidden, precision)
     advp = None if adv is None else C.byref(adv)
     if g.is_cuda:
         if g.device.index != bundle.device or (a is not None and a.device != g.device):
@@ -91,7 +102,7 @@ def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_ra
 
 def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, first_index=0,
                    adv_master=None, adv_sigma=None, phi, fee_rate=0.0, hidden=32,
-                   units_per_lane=0, warps_per_cta=0):
+                   units_per_lane=0, warps_per_cta=0, precision=None):
     """Evaluate children ``first_index .. first_index+count-1`` of ``master`` without ever storing
     them: child i = master + sigma*N(0,1)[Philox(seed, generation, i)] is generated inside the
     kernel (device-resident ``ask``, models/model.py:65-71).  ``master`` (and ``adv_master``) are
@@ -112,27 +123,32 @@ def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, fi
         adv = _lib.Population(32, 0, count, None, am.data_ptr(), float(sigma if adv_sigma is None else adv_sigma),
                               0.0, int(seed) ^ ADV_SEED_FLIP, int(generation), int(first_index))
         advp = C.byref(adv)
-    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta, hidden)
+    prm = _params(phi, fee_rate, units_per_lane, warps_per_cta, hidden, precision)
     _lib.check(_lib.lib().sgmm_rollout_population(bundle.handle, C.byref(mm), advp, C.byref(prm),
                                                   fit.data_ptr(), trd.data_ptr(), _stream(bundle.device)))
     return fit, trd
 
 
-def rollout_spec256_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0):
-    """Tensor-core (H=256, bf16) rollout with its audit outputs: returns ``(fitness, trades,
-    raw_table float32[P,T,5,2], act_trace int32[P,T,2])`` as CUDA tensors."""
-    g = _as_f32_matrix(genomes, genome_len(256)).to(f"cuda:{bundle.device}")
+def rollout_tc_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0, hidden=32, group=0):
+    """Tensor-core rollout (hidden=32: sgmm_tc32.cu, hidden=256: sgmm_spec256.cu) with its audit
+    outputs: returns ``(fitness, trades, raw_table float32[P,T,5,2], act_trace int32[P,T,2])`` as
+    CUDA tensors -- the policy outputs for every (bar, inventory) and the offsets actually taken."""
+    g = _as_f32_matrix(genomes, genome_len(hidden)).to(f"cuda:{bundle.device}")
     P, T = g.shape[0], bundle.T
     fit = torch.empty(P, dtype=torch.float64, device=g.device)
     trd = torch.empty(P, dtype=torch.int32, device=g.device)
     raw = torch.zeros(P, T, 5, 2, dtype=torch.float32, device=g.device)
     act = torch.zeros(P, T, 2, dtype=torch.int32, device=g.device)
-    mm = _lib.Population(256, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
-    prm = _params(phi, fee_rate, hidden=256)
+    mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    prm = _params(phi, fee_rate, units_per_lane=group, hidden=hidden, precision=PRECISION_BF16)
     _lib.check(_lib.lib().sgmm_rollout_spec256_audit(bundle.handle, C.byref(mm), C.byref(prm), fit.data_ptr(),
                                                      trd.data_ptr(), raw.data_ptr(), act.data_ptr(),
                                                      _stream(bundle.device)))
     return fit, trd, raw, act
+
+
+def rollout_spec256_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0):
+    return rollout_tc_audit(bundle, genomes, phi=phi, fee_rate=fee_rate, hidden=256)
 
 
 _TRACE_I32 = ("off_a", "off_b", "adv_a", "adv_b", "fill_buy", "fill_sell", "inventory")

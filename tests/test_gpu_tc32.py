@@ -1,0 +1,163 @@
+"""GPU (-m gpu): the H=32 tensor-core rollout (sgmm_tc32.cu: all three policy layers on tcgen05, A operands
+chained through tensor memory, bf16 inputs / fp32 accumulate).  Parity is stated in two halves, as for
+the H=256 kernel:
+
+  (1) POLICY OUTPUTS vs the fp32 oracle (SGMM-F32 order, oracle/sgmm_oracle.c) for EVERY (bar,
+      inventory) pair: |d(raw*5)| <= TAU_TICKS, and the rounded offsets are identical wherever the
+      oracle's own distance to a rounding boundary exceeds TAU_TICKS;
+  (2) GIVEN the offsets the kernel took, fills, inventory, trade count, rewards and fitness are
+      BIT-IDENTICAL to the oracle's env (teacher-forced replay of the kernel's action trace).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TAU_TICKS = 0.12         # stated bf16 tolerance on raw*5 (ticks) for offsets spanning +-10 ticks; measured max is printed
+
+
+@pytest.fixture(scope="module")
+def sg():
+    assert torch.cuda.is_available()
+    import sgmm_b200
+    return sgmm_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _setup(sg, orc, days, first_day, P, seed, T=None, out_scale=6.0):
+    from sgmm_b200 import synthetic
+    bundle = synthetic.synthetic_bundle(days, first_day=first_day)
+    if T is not None:
+        bundle = tuple(a[:T] for a in bundle)
+    stats = synthetic.train_stats_of(synthetic.synthetic_bundle(days, first_day=first_day))
+    z1, z2 = orc.normalise(bundle, stats)
+    bun = sg.Bundle.from_arrays(bundle, stats, 0.001)
+    master, genomes = synthetic.policy_like_genomes(P, hidden=32, seed=seed, out_scale=out_scale, out_bias=(0.1, 0.1))
+    return bundle, (z1, z2) + bundle[2:], bun, master, genomes
+
+
+def _audit(orc, bz, genomes, raw, T):
+    worst, flips_outside = 0.0, 0
+    for i in range(genomes.shape[0]):
+        for t in range(T):
+            for iv in range(5):
+                want = orc.mlp_forward(genomes[i], [bz[0][t], bz[1][t], (iv - 2) / 2.0], hidden=32)
+                q_o = want * np.float32(5.0)
+                q_k = raw[i, t, iv] * np.float32(5.0)
+                worst = max(worst, float(np.max(np.abs(q_o - q_k))))
+                margin = np.abs(np.abs(q_o - np.floor(q_o)) - 0.5)
+                flips_outside += int(np.sum((np.rint(q_o) != np.rint(q_k)) & (margin > TAU_TICKS)))
+    return worst, flips_outside
+
+
+@pytest.mark.parametrize("fee", [0.0, 3e-4])
+def test_policy_outputs_within_tolerance_and_env_bit_exact(sg, orc, fee):
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 90, 5, seed=11)
+    T = bun.T
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, fee_rate=fee, hidden=32)
+    fit, trd, raw, act = fit.cpu().numpy(), trd.cpu().numpy(), raw.cpu().numpy(), act.cpu().numpy()
+    worst, flips_outside = _audit(orc, bz, genomes, raw, T)
+    for i in range(genomes.shape[0]):
+        fo, to, tro = orc.rollout(None, None, bz, 1e-4, 0.001, fee, forced_actions=act[i], trace=True)
+        assert fo == fit[i] and to == trd[i], (i, fo, fit[i], to, trd[i])
+        inv_before = np.concatenate([[0], tro["inventory"][:-1]])
+        taken = np.rint(raw[i, np.arange(T), inv_before + 2] * np.float32(5.0)).astype(np.int32)
+        assert np.array_equal(taken, act[i])
+    print(f"max |d(raw*5)| = {worst:.4g} ticks (tolerance {TAU_TICKS})")
+    assert worst <= TAU_TICKS
+    assert flips_outside == 0
+
+
+@pytest.mark.parametrize("T,P,group", [(1, 3, 0), (24, 40, 0), (25, 150, 0), (26, 17, 16), (51, 33, 6), (130, 5, 2), (240, 300, 0)])
+def test_ragged_lengths_groups_and_many_individuals(sg, orc, T, P, group):
+    """Tail chunks, partial groups (P not a multiple of the group), several groups per CTA."""
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 91, P, seed=T, T=T)
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, hidden=32, group=group)
+    f2, t2 = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, precision="bf16")
+    assert torch.equal(f2, fit) and torch.equal(t2, trd)
+    fit, trd, act = fit.cpu().numpy(), trd.cpu().numpy(), act.cpu().numpy()
+    for i in range(0, P, max(1, P // 9)):
+        fo, to = orc.rollout(None, None, bz, 1e-4, 0.001, 0.0, forced_actions=act[i])
+        assert fo == fit[i] and to == trd[i], (i, fo, fit[i])
+    # the last individual exercises the partial group
+    fo, to = orc.rollout(None, None, bz, 1e-4, 0.001, 0.0, forced_actions=act[P - 1])
+    assert fo == fit[P - 1] and to == trd[P - 1]
+
+
+def test_empty_bundle_and_host_entry(sg, orc):
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 94, 6, seed=2, T=0)
+    f, t = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, precision="bf16")
+    assert np.array_equal(f.cpu().numpy(), np.full(6, -50.0)) and int(t.sum()) == 0      # drl_engine.py:64-65
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 94, 37, seed=2)
+    fd, td = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, precision="bf16")
+    fh, th = sg.rollout_population(bun, genomes, phi=1e-4, precision="bf16")               # host pointers end to end
+    assert np.array_equal(fd.cpu().numpy(), fh) and np.array_equal(td.cpu().numpy(), th)
+
+
+def test_closed_loop_diverges_from_fp32_oracle_only_at_near_ties(sg, orc):
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 2, 92, 8, seed=5)
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, hidden=32)
+    fit, trd, act = fit.cpu().numpy(), trd.cpu().numpy(), act.cpu().numpy()
+    identical = 0
+    for i in range(genomes.shape[0]):
+        fo, to, tro = orc.rollout(genomes[i], None, bz, 1e-4, 0.001, 0.0, hidden=32, trace=True)
+        diff = (tro["off_a"] != act[i, :, 0]) | (tro["off_b"] != act[i, :, 1])
+        if not diff.any():
+            identical += 1
+            assert fo == fit[i] and to == trd[i]
+            continue
+        t = int(np.argmax(diff))
+        q = np.array([tro["raw_a"][t], tro["raw_b"][t]], np.float32) * np.float32(5.0)
+        margin = np.min(np.abs(np.abs(q - np.floor(q)) - 0.5))
+        assert margin <= TAU_TICKS, (i, t, q)
+    print("closed-loop trajectories identical to the fp32 oracle:", identical, "of", genomes.shape[0])
+
+
+def test_seeded_children_match_explicit_genomes(sg, orc):
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 93, 1, seed=3, T=100)
+    kids = np.stack([orc.mutate(master, 0.05, 77, 4, 10 + i) for i in range(21)])
+    f_exp, t_exp = sg.rollout_population(bun, torch.from_numpy(kids).cuda(), phi=1e-4, precision="bf16")
+    f_seed, t_seed = sg.rollout_seeded(bun, torch.from_numpy(master).cuda(), count=21, sigma=0.05, seed=77,
+                                       generation=4, first_index=10, phi=1e-4, precision="bf16")
+    assert torch.equal(f_exp, f_seed) and torch.equal(t_exp, t_seed)
+
+
+def test_golden_arl_checkpoint_audit_set(sg, orc):
+    """The fixed audit set: the reference's shipped ARL agent on its own 960-bar test bundle (tests/golden,
+    960/960 recorded actions).  On the (bar, inventory) pairs the recorded run visited, the tensor-core
+    policy outputs are within tolerance of the fp32 oracle; a recorded offset may flip only where the
+    oracle's own raw*5 is within TAU_TICKS of a rounding boundary; flips are counted and reported."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    c = np.load(os.path.join(here, "golden", "checkpoints.npz"))
+    b = np.load(os.path.join(here, "golden", "backtest_510300.npz"))
+    g = c["510300_with_adv"]
+    s1, s2 = b["arl.s1_pred"], b["arl.s2_pred"]
+    z1 = ((s1 - c["train_stats_s1_m"][()]) / c["train_stats_s1_s"][()]).astype(np.float32)
+    z2 = ((s2 - c["train_stats_s2_m"][()]) / c["train_stats_s2_s"][()]).astype(np.float32)
+    fb, fs = b["arl.fill_buy"], b["arl.fill_sell"]
+    my_ask = b["arl.ask"] + b["arl.off_a"] * 0.001
+    my_bid = b["arl.bid"] - b["arl.off_b"] * 0.001
+    bun = sg.Bundle(z1, z2, b["arl.mid"], b["arl.ask"], b["arl.bid"],
+                    np.where(fs == 1, my_ask, my_ask - 0.0005), np.where(fb == 1, my_bid, my_bid + 0.0005), 0.001)
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, g.reshape(1, -1), phi=1e-4, hidden=32)
+    raw, act = raw.cpu().numpy()[0], act.cpu().numpy()[0]
+    inv_prev = np.concatenate([[0], b["arl.inventory"][:-1]])
+    worst, flips, flips_outside = 0.0, 0, 0
+    for t in range(960):
+        want = orc.mlp_forward(g, [z1[t], z2[t], inv_prev[t] / 2.0])
+        q_o, q_k = want * np.float32(5.0), raw[t, inv_prev[t] + 2] * np.float32(5.0)
+        worst = max(worst, float(np.max(np.abs(q_o - q_k))))
+        margin = np.abs(np.abs(q_o - np.floor(q_o)) - 0.5)
+        rec = np.array([b["arl.off_a"][t], b["arl.off_b"][t]])
+        flips += int(np.sum(np.rint(q_k) != rec))
+        flips_outside += int(np.sum((np.rint(q_k) != rec) & (margin > TAU_TICKS)))
+    print(f"golden ARL audit set: max |d(raw*5)| = {worst:.4g} ticks, {flips} of 1920 recorded offsets flip "
+          f"(all within {TAU_TICKS} tick of a rounding boundary of the fp32 result)")
+    assert worst <= TAU_TICKS and flips_outside == 0
