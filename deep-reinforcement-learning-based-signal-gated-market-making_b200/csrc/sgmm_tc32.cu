@@ -55,11 +55,15 @@ constexpr int WARP_L1 = 24, WARP_L2 = 25, WARP_L3 = 26;     // warp 27 = walker
 constexpr int NUM_THREADS = 896;
 constexpr uint32_t TMEM_COLS = 512;
 // TMEM column map.  The pipeline moves UNITS of two tiles (the same 25-bar chunk for two individuals of the
-// group), so that every mbarrier round trip and every issuer iteration is shared by two tiles.  Two unit
-// buffers of 256 columns each; inside a buffer tile j of the unit sits at + j * S_*:
-constexpr uint32_t BUF_COLS = 256;
-constexpr uint32_t C_D1 = 0, C_A2 = 64, C_D2 = 112, C_A3 = 176, C_D3 = 224;
-constexpr uint32_t S_D = 32, S_A = 24, S_D3 = 16;
+// group), so that every mbarrier round trip and every issuer iteration is shared by two tiles.  Three unit
+// buffers of 160 columns; inside a buffer tile j of the unit sits at + j * S_*:
+//   R1 (64 columns)  D1 fp32 [128 x 32] per tile, overwritten IN PLACE by A2 = relu(D1) as bf16 pairs (16 columns)
+//   R2 (64 columns)  D2 fp32, overwritten in place by A3
+//   R3 (32 columns)  D3 fp32 [128 x 16] per tile
+// plus 8 constant columns [1 1 0 ... 0] (bf16 pairs): the A operand of every bias K-step.
+constexpr uint32_t NBUF = 3, BUF_COLS = 160;
+constexpr uint32_t C_R1 = 0, C_R2 = 64, C_R3 = 128, C_ONE = 480;
+constexpr uint32_t S_D = 32, S_D3 = 16;
 constexpr int64_t G32 = 1250;
 constexpr int TAB_R_STRIDE = TILE_ROWS + 1;    // doubles per individual: 258 words -> walker lanes hit distinct banks
 constexpr int TAB_N_STRIDE = TILE_BARS * 8;    // bytes per individual: 50 words -> distinct bank pairs
@@ -72,9 +76,10 @@ struct Smem {
     double tab_r[2][GMAX][TAB_R_STRIDE];       // reward of (bar, inventory) rows
     uint8_t tab_n[2][GMAX][TAB_N_STRIDE];      // next inventory index | traded << 3, 8 bytes per bar
     uint64_t a1_full[A1_STAGES], a1_empty[A1_STAGES];
-    // per layer and TMEM buffer: ready = inputs of the MMA are in place (A written, previous D drained),
-    // done = tcgen05.commit of the layer's MMAs (D complete AND the A buffer it read is free again)
-    uint64_t l1_ready[2], l1_done[2], l2_ready[2], l2_done[2], l3_ready[2], l3_done[2];
+    // per TMEM buffer.  l*_done = tcgen05.commit of the layer's MMAs: its accumulator is complete AND the A
+    // operand it read (which lives where the previous layer's accumulator was) may be overwritten.
+    // a2_ready = E1 wrote A2 (4 warps); l3_ready = E2 wrote A3 (4) + E3 drained the previous D3 (4).
+    uint64_t l1_done[3], a2_ready[3], l2_done[3], l3_ready[3], l3_done[3];
     uint64_t tab_full[2], tab_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
@@ -281,6 +286,100 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// position of a unit in the pipeline: TMEM buffer (unit index mod 3) and mbarrier phase parity (use count & 1)
+struct Slot {
+    uint32_t b, par, col;            // buffer, parity, TMEM column offset of the buffer (b * BUF_COLS)
+    __device__ __forceinline__ void init(uint32_t i) { b = i % NBUF; par = (i / NBUF) & 1u; col = b * BUF_COLS; }
+    __device__ __forceinline__ void advance(uint32_t n)                                          // n <= NBUF
+    {
+        b += n; col += n * BUF_COLS;
+        if (b >= NBUF) { b -= NBUF; col -= NBUF * BUF_COLS; par ^= 1u; }
+    }
+};
+
+// 64-bit tcgen05 operand words from 32-bit halves (the low word carries the 14-bit start address >> 4)
+__device__ __forceinline__ void umma_ts2(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t id, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t id, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %6, 0;\nmov.b64 ad, {%1, %2};\nmov.b64 bd, {%3, %4};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n}\n"
+                 ::"r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }     // version 1 at bit 46
+
+// L2 / L3 issuer: a converged warp; one elected lane issues the six MMAs of a unit and one commit
+template <int LAYER>
+__device__ __forceinline__ void issue_role(Smem& sm, uint32_t tmem_base, uint32_t gt, uint32_t nunits, uint32_t UG)
+{
+    constexpr uint32_t ID = LAYER == 2 ? idesc(32) : idesc(16);
+    constexpr uint32_t DSTEP = LAYER == 2 ? S_D : S_D3;
+    constexpr uint32_t BSTEP = (uint32_t)((LAYER == 2 ? B2_BYTES : B3_BYTES) >> 4);
+    uint64_t* ready = LAYER == 2 ? sm.a2_ready : sm.l3_ready;     // A operand written (L3: and previous D3 drained)
+    uint64_t* done = LAYER == 2 ? sm.l2_done : sm.l3_done;
+    const uint32_t d0 = tmem_base + (LAYER == 2 ? C_R2 : C_R3), a0 = tmem_base + (LAYER == 2 ? C_R1 : C_R2);
+    const uint32_t one = tmem_base + C_ONE;
+    const uint32_t blo0 = desc_lo(LAYER == 2 ? smem_u32(sm.b2[0]) : smem_u32(sm.b3[0]), 128), bhi = desc_hi(768);
+    uint32_t u = 0, blo = blo0;
+    Slot sl; sl.init(gt);
+#pragma unroll 1
+    for (uint32_t it = 0; it < nunits; ++it) {
+        mbar_wait(&ready[sl.b], sl.par);
+        if (LAYER == 2) mbar_wait(&sm.l3_done[sl.b], sl.par ^ 1u);    // layer 3 has read the A operand that lives where D2 goes
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t d = d0 + sl.col, aa = a0 + sl.col;
+            umma_ts2(d, aa, blo, bhi, ID, 0u);
+            umma_ts2(d, aa + 8, blo + 16, bhi, ID, 1u);                       // +256 B per K=16 step
+            umma_ts2(d, one, blo + 32, bhi, ID, 1u);                          // bias step: A = the constant [1 1 0 ...] columns
+            umma_ts2(d + DSTEP, aa + S_D, blo + BSTEP, bhi, ID, 0u);          // second tile of the unit
+            umma_ts2(d + DSTEP, aa + S_D + 8, blo + BSTEP + 16, bhi, ID, 1u);
+            umma_ts2(d + DSTEP, one, blo + BSTEP + 32, bhi, ID, 1u);
+            umma_commit(&done[sl.b]);
+        }
+        __syncwarp();
+        sl.advance(1);
+        blo += 2 * BSTEP;
+        if (++u == UG) { u = 0; blo = blo0; }
+    }
+}
+
+// E1 / E2: accumulator (fp32, TMEM) -> ReLU -> bf16 pairs written back IN PLACE as the next layer's A operand
+template <int LAYER>
+__device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint32_t gt, uint32_t it0, uint32_t nunits, int lane)
+{
+    uint64_t* done_in = LAYER == 1 ? sm.l1_done : sm.l2_done;        // accumulator complete
+    uint64_t* filled = LAYER == 1 ? sm.a2_ready : sm.l3_ready;       // A operand written
+    const uint32_t r_addr = lane_addr + (LAYER == 1 ? C_R1 : C_R2);
+    Slot sl; sl.init(gt + it0);
+#pragma unroll 1
+    for (uint32_t it = it0; it < nunits; it += 2, sl.advance(2)) {
+        const uint32_t addr = r_addr + sl.col;
+        mbar_wait(&done_in[sl.b], sl.par);
+        tc_fence_after();
+        uint32_t v[32], p[16];
+        tmem_ld32(addr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        tmem_ld32(addr + S_D, v);                                    // second tile of the unit
+        tmem_st16(addr, p);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        tmem_st16(addr + S_D, p);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&filled[sl.b]);
+    }
+}
+
 template <bool FEE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
 {
@@ -296,12 +395,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
 
     if (tid == 0) {
         for (int i = 0; i < A1_STAGES; ++i) { mbar_init(&sm.a1_full[i], 1); mbar_init(&sm.a1_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.l1_ready[i], 4); mbar_init(&sm.l1_done[i], 1);
-            mbar_init(&sm.l2_ready[i], 8); mbar_init(&sm.l2_done[i], 1);
-            mbar_init(&sm.l3_ready[i], 8); mbar_init(&sm.l3_done[i], 1);
-            mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1);
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(&sm.l1_done[i], 1); mbar_init(&sm.a2_ready[i], 4);
+            mbar_init(&sm.l2_done[i], 1); mbar_init(&sm.l3_ready[i], 8); mbar_init(&sm.l3_done[i], 1);
         }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_L1) {
@@ -316,19 +414,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may touch (warp % 4)
-    const uint32_t pset = (uint32_t)(warp >> 2) & 1u;     // epilogue warps: which of the two TMEM buffers (tile parity) is theirs
+    const uint32_t pset = (uint32_t)(warp >> 2) & 1u;     // epilogue warps: even or odd units
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    if (warp < 16) {
-        // constant tail of the A2 / A3 operands: K slots 32, 33 = 1.0 (bias rows of B2 / B3), 34..47 = 0
-        const uint32_t cbase = (warp < 8 ? C_A2 : C_A3) + pset * BUF_COLS;
+    if (warp < 4) {
+        // the constant K-step shared by every layer-2 / layer-3 MMA: K slots 32, 33 = 1.0 (they meet the
+        // bias rows of B2 / B3), 34..47 = 0
         uint32_t c[8] = {0x3F803F80u, 0, 0, 0, 0, 0, 0, 0};
-        tmem_st8(lane_addr + cbase + 16, c);
-        tmem_st8(lane_addr + cbase + S_A + 16, c);
+        tmem_st8(lane_addr + C_ONE, c);
         tmem_st_wait();
     }
-    // "accumulator drained" half of the first use of the l2 / l3 ready barriers
-    if (warp >= 8 && warp < 16 && lane == 0) mbar_arrive(&sm.l2_ready[pset]);
-    if (warp >= 16 && warp < 24 && lane == 0) mbar_arrive(&sm.l3_ready[pset]);
+    // "previous accumulator drained" half of the first use of the l3_ready barriers
+    if (warp >= 16 && warp < 20 && lane == 0) { for (int i = 0; i < NBUF; ++i) mbar_arrive(&sm.l3_ready[i]); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -364,50 +460,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        // first unit of this group that lands in this warp's TMEM buffer
+        // first unit of this group that belongs to this warp's set (even / odd global unit index)
         const uint32_t it0 = ((gt & 1u) == pset) ? 0u : 1u;
 
-        if (warp < 16) {
-            // =========================== E1 / E2 : D -> relu -> bf16 -> next A ====================
-            const bool first = warp < 8;
-            uint64_t* done_in = first ? &sm.l1_done[pset] : &sm.l2_done[pset];       // accumulator complete
-            uint64_t* drained = first ? &sm.l1_ready[pset] : &sm.l2_ready[pset];     // accumulator read out
-            uint64_t* done_out = first ? &sm.l2_done[pset] : &sm.l3_done[pset];      // MMAs that read the A buffer retired
-            uint64_t* filled = first ? &sm.l2_ready[pset] : &sm.l3_ready[pset];      // A buffer written
-            const uint32_t d_addr = lane_addr + (first ? C_D1 : C_D2) + pset * BUF_COLS;
-            const uint32_t a_addr = lane_addr + (first ? C_A2 : C_A3) + pset * BUF_COLS;
-#pragma unroll 1
-            for (uint32_t it = it0; it < nunits; it += 2) {
-                const uint32_t par = ((gt + it) >> 1) & 1u;
-                mbar_wait(done_in, par);
-                tc_fence_after();
-                uint32_t v[32], p[16];
-                tmem_ld32(d_addr, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                tmem_ld32(d_addr + S_D, v);                                  // second tile of the unit
-                mbar_wait(done_out, par ^ 1u);                               // the MMAs that read this A buffer have retired
-                tc_fence_after();
-                tmem_st16(a_addr, p);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(drained);                         // accumulator read out
-#pragma unroll
-                for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                tmem_st16(a_addr + S_A, p);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(filled);
-            }
+        if (warp < 8) {
+            convert_role<1>(sm, lane_addr, gt, it0, nunits, lane);
+        } else if (warp < 16) {
+            convert_role<2>(sm, lane_addr, gt, it0, nunits, lane);
         } else if (warp < 24) {
             // =========================== E3 : offsets, speculative env step, table ================
             const int row = quarter * 32 + lane;
             const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
             const bool row_ok = row < TILE_BARS * 5;
-            const uint32_t d_addr = lane_addr + C_D3 + pset * BUF_COLS;
+            const uint32_t d_addr = lane_addr + C_R3;
             int2 kth = make_int2(0, 0), kth_n = make_int2(0, 0);
             double2 ab = make_double2(0., 0.), ab_n = make_double2(0., 0.);
             double mid = 0.0, mid_n = 0.0;
@@ -419,42 +484,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                     m = __ldg(&a.px[t].mid_next);
                 }
             };
-            uint32_t c_cur = 0xFFFFFFFFu;
-            if (it0 < nunits) load_bar(it0 / UG, kth_n, ab_n, mid_n);
+            // this warp's units: it0, it0+2, ...; unit -> (chunk c, pair position up) tracked incrementally
+            uint32_t c = it0 / UG, up = it0 - c * UG;
+            bool fresh = true;                                                        // first unit of a chunk for this warp
+            if (it0 < nunits) load_bar(c, kth_n, ab_n, mid_n);
+            Slot sl; sl.init(gt + it0);
+            const uint32_t cstep = UG == 1 ? 2u : 1u;                                 // distance to the next chunk this warp sees
+            double* const tab_r0 = &sm.tab_r[0][0][row];
+            uint8_t* const tab_n0 = &sm.tab_n[0][0][tl * 8 + iv];
+            const int inv = iv - 2;
 #pragma unroll 1
-            for (uint32_t it = it0; it < nunits; it += 2) {
-                const uint32_t par = ((gt + it) >> 1) & 1u;
-                const uint32_t c = it / UG;
-                const int g0 = (int)(it - c * UG) * 2;
-                const uint32_t q = gc + c, cbuf = q & 1u, cpar = (q >> 1) & 1u;
-                const int64_t t = (int64_t)c * TILE_BARS + tl;
-                const bool valid = row_ok && t < T;
-                if (c != c_cur) {                                                     // this warp's first unit of chunk c
-                    c_cur = c;
+            for (uint32_t it = it0; it < nunits; it += 2, sl.advance(2)) {
+                const uint32_t q = gc + c, cbuf = q & 1u;
+                const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
+                if (fresh) {
+                    fresh = false;
                     kth = kth_n; ab = ab_n; mid = mid_n;
-                    const uint32_t cn = c + (UG == 1 ? 2u : 1u);                      // the next chunk this warp will see
-                    if (cn < nchunks) load_bar(cn, kth_n, ab_n, mid_n);               // prefetch its bars
-                    mbar_wait(&sm.tab_empty[cbuf], cpar ^ 1u);                        // walker has left this table buffer
+                    if (c + cstep < nchunks) load_bar(c + cstep, kth_n, ab_n, mid_n);       // prefetch its bars
+                    mbar_wait(&sm.tab_empty[cbuf], ((q >> 1) & 1u) ^ 1u);                   // walker has left this table buffer
                 }
-                mbar_wait(&sm.l3_done[pset], par);
+                mbar_wait(&sm.l3_done[sl.b], sl.par);
                 tc_fence_after();
                 uint32_t v[2][4];
-                tmem_ld4(d_addr, v[0]);
-                tmem_ld4(d_addr + S_D3, v[1]);
+                tmem_ld4(d_addr + sl.col, v[0]);
+                tmem_ld4(d_addr + sl.col + S_D3, v[1]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.l3_ready[pset]);
+                if (lane == 0) mbar_arrive(&sm.l3_ready[sl.b]);                              // accumulator drained
+                double* tr = tab_r0 + (cbuf * GMAX + up * 2u) * TAB_R_STRIDE;
+                uint8_t* tn = tab_n0 + (cbuf * GMAX + up * 2u) * TAB_N_STRIDE;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int g = g0 + j;
                     const float ra = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));      // hi + lo halves of W3
                     const float rb = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
                     const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));                            // drl_engine.py:39
                     const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
                     if (valid) {
                         // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                        const int inv = iv - 2;
                         const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
                         const bool fs = (inv > -2) && (ka < kth.x);              // :35,:38
                         const double my_ask = add_rn(ab.x, mul_rn((double)ka, a.tick));
@@ -469,12 +536,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                         pnl = fs ? add_rn(pnl, leg_s) : pnl;
                         const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
                         const int ai = ninv < 0 ? -ninv : ninv;
-                        sm.tab_r[cbuf][g][row] = sub_rn(pnl, mul_rn(a.phi, (double)ai));           // :57-58
-                        sm.tab_n[cbuf][g][tl * 8 + iv] = (uint8_t)((ninv + 2) | ((fb || fs) ? 8 : 0));
+                        tr[j * TAB_R_STRIDE] = sub_rn(pnl, mul_rn(a.phi, (double)ai));             // :57-58
+                        tn[j * TAB_N_STRIDE] = (uint8_t)((ninv + 2) | ((fb || fs) ? 8 : 0));
                         if (a.raw_table) {
-                            const int64_t ind = grp * G + g;
+                            const int64_t ind = grp * G + (int64_t)(up * 2u) + j;
                             if (ind < pop.count) {
-                                float* o = a.raw_table + (((int64_t)ind * T + t) * 5 + iv) * 2;
+                                float* o = a.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
                                 __stcg(o, ra); __stcg(o + 1, rb);
                             }
                         }
@@ -482,6 +549,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.tab_full[cbuf]);
+                up += 2;
+                while (up >= UG) { up -= UG; ++c; fresh = true; }        // (UG == 1: two chunks ahead)
             }
         } else if (warp == WARP_L1) {
             // =========================== L1 ISSUER + A1 TMA PRODUCER ===============================
@@ -496,65 +565,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 __syncwarp();
             };
             for (uint32_t c = 0; c < nchunks && c < (uint32_t)(A1_STAGES - 1); ++c) load_a1(c);
-            constexpr uint32_t ID32 = idesc(32);
-            const uint64_t b1d0 = make_desc(smem_u32(sm.b1[0]), 128, 256);
-            uint32_t c1 = 0, u1 = 0;
-            uint64_t ad = 0;
+            // both tiles of a unit share the A1 tile and their B1 operands are adjacent in shared memory
+            // (4 row groups of 256 B each): ONE M=128, N=64, K=16 MMA fills D1 of both tiles
+            constexpr uint32_t ID64 = idesc(64);
+            const uint32_t b1lo0 = desc_lo(smem_u32(sm.b1[0]), 128), dhi = desc_hi(256);
+            uint32_t c1 = 0, u1 = 0, blo = b1lo0, alo = 0;
+            Slot sl; sl.init(gt);
 #pragma unroll 1
             for (uint32_t it = 0; it < nunits; ++it) {
-                const uint32_t i = gt + it, buf = i & 1u, par = (i >> 1) & 1u;
-                const uint32_t q = gc + c1, slot = q % A1_STAGES, use = q / A1_STAGES;
+                const uint32_t q = gc + c1, slot = q % A1_STAGES;
                 if (u1 == 0) {
                     if (c1 + A1_STAGES - 1 < nchunks) load_a1(c1 + A1_STAGES - 1);
-                    mbar_wait(&sm.a1_full[slot], use & 1u);
-                    ad = make_desc(smem_u32(sm.a1[slot]), 128, 256);
+                    mbar_wait(&sm.a1_full[slot], (q / A1_STAGES) & 1u);
+                    alo = desc_lo(smem_u32(sm.a1[slot]), 128);
                 }
-                mbar_wait(&sm.l1_ready[buf], par ^ 1u);
+                mbar_wait(&sm.l2_done[sl.b], sl.par ^ 1u);            // layer 2 of the unit that used this buffer before has read its A operand
                 tc_fence_after();
                 const bool last = (u1 + 1 == UG);
                 if (elect_one()) {
-                    const uint64_t bd = b1d0 + (uint64_t)(u1 * 2u * (uint32_t)(B1_BYTES >> 4));
-                    const uint32_t d = tmem_base + C_D1 + buf * BUF_COLS;
-                    umma_ss(d, ad, bd, ID32, 0u);
-                    umma_ss(d + S_D, ad, bd + (uint64_t)(B1_BYTES >> 4), ID32, 0u);
-                    umma_commit(&sm.l1_done[buf]);
+                    umma_ss2(tmem_base + C_R1 + sl.col, alo, dhi, blo, dhi, ID64, 0u);
+                    umma_commit(&sm.l1_done[sl.b]);
                     if (last) umma_commit(&sm.a1_empty[slot]);
                 }
                 __syncwarp();
-                if (last) { u1 = 0; ++c1; } else ++u1;
+                sl.advance(1);
+                blo += 2u * (uint32_t)(B1_BYTES >> 4);
+                if (last) { u1 = 0; ++c1; blo = b1lo0; } else ++u1;
             }
-        } else if (warp == WARP_L2 || warp == WARP_L3) {
-            // =========================== L2 / L3 ISSUER ============================================
-            const bool second = warp == WARP_L2;
-            uint64_t* ready = second ? sm.l2_ready : sm.l3_ready;
-            uint64_t* done = second ? sm.l2_done : sm.l3_done;
-            const uint32_t id = second ? idesc(32) : idesc(16);
-            const uint32_t d_col = tmem_base + (second ? C_D2 : C_D3), d_step = second ? S_D : S_D3;
-            const uint32_t a_col = tmem_base + (second ? C_A2 : C_A3);
-            const uint64_t bd0 = make_desc(second ? smem_u32(sm.b2[0]) : smem_u32(sm.b3[0]), 128, 768);
-            const uint32_t bstep = (uint32_t)((second ? B2_BYTES : B3_BYTES) >> 4);
-            uint32_t u = 0;
-#pragma unroll 1
-            for (uint32_t it = 0; it < nunits; ++it) {
-                const uint32_t i = gt + it, buf = i & 1u, par = (i >> 1) & 1u;
-                mbar_wait(&ready[buf], par);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t bd = bd0 + (uint64_t)(u * 2u * bstep);
-                    const uint32_t d = d_col + buf * BUF_COLS, aa = a_col + buf * BUF_COLS;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint64_t bj = bd + (uint64_t)((uint32_t)j * bstep);
-                        const uint32_t dj = d + (uint32_t)j * d_step, aj = aa + (uint32_t)j * S_A;
-                        umma_ts(dj, aj, bj, id, 0u);
-                        umma_ts(dj, aj + 8, bj + 16, id, 1u);          // +256 B per K=16 step
-                        umma_ts(dj, aj + 16, bj + 32, id, 1u);
-                    }
-                    umma_commit(&done[buf]);
-                }
-                __syncwarp();
-                if (++u == UG) u = 0;
-            }
+        } else if (warp == WARP_L2) {
+            issue_role<2>(sm, tmem_base, gt, nunits, UG);
+        } else if (warp == WARP_L3) {
+            issue_role<3>(sm, tmem_base, gt, nunits, UG);
         } else {
             // =========================== WALKER : one lane per individual ==========================
             const int g = lane;
