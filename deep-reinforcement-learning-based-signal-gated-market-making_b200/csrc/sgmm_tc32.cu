@@ -20,12 +20,13 @@
 // One persistent CTA per SM works on a GROUP of up to 16 individuals in lockstep over time: the A1 tile
 // of a 25-bar chunk is loaded once and multiplied with every individual's weights (a grouped GEMM:
 // per-individual B operands, shared A operand), 16 walker lanes advance 16 independent automata.
-//   warps 0-7   E1 : D1 -> relu -> bf16 -> A2   (warp % 4 = TMEM lane quarter; warps 0-3 own TMEM buffer 0 =
-//   warps 8-15  E2 : D2 -> relu -> bf16 -> A3    even tiles, warps 4-7 buffer 1 = odd tiles, likewise below)
-//   warps 16-23 E3 : D3 -> offsets -> speculative env step -> table
-//   warps 24-26 L1 / L2 / L3 issuers: a converged warp each, one elected lane issues tcgen05.mma + commit
+//   warps 0-3   E1 : D1 -> relu -> bf16 -> A2 (in place)      (warp % 4 = TMEM lane quarter)
+//   warps 4-7   E2 : D2 -> relu -> bf16 -> A3 (in place)
+//   warps 8-19  E3 : D3 -> offsets -> speculative env step -> table; three sets of four warps, set s owns
+//                    TMEM buffer s (the fp64 step is a long dependency chain: latency, not issue slots)
+//   warps 20-22 L1 / L2 / L3 issuers: a converged warp each, one elected lane issues tcgen05.mma + commit
 //               (three independent issue streams; the L1 warp also feeds the A1 ring with TMA bulk copies)
-//   warp  27    walker
+//   warp  23    walker
 // Every TMEM region is double-buffered; per layer and buffer one "ready" mbarrier (A written + D drained)
 // and one "done" mbarrier (tcgen05.commit).
 //
@@ -33,6 +34,7 @@
 // tests/test_gpu_tc32.py states the tolerance against the fp32 oracle and checks that GIVEN the offsets
 // the kernel took, fills / inventory / trades / rewards / fitness are bit-identical to the oracle.
 #include <cuda_bf16.h>
+#include <cstdio>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
 #include "sgmm_step_core.h"
@@ -51,8 +53,8 @@ constexpr int B1_BYTES = H * K1 * 2;           // 1024
 constexpr int B2_BYTES = H * K2 * 2;           // 3072
 constexpr int B3_BYTES = 16 * K2 * 2;          // 1536
 constexpr int A1_STAGES = 4;
-constexpr int WARP_L1 = 24, WARP_L2 = 25, WARP_L3 = 26;     // warp 27 = walker
-constexpr int NUM_THREADS = 896;
+constexpr int WARP_L1 = 20, WARP_L2 = 21, WARP_L3 = 22;     // warp 23 = walker
+constexpr int NUM_THREADS = 768;
 constexpr uint32_t TMEM_COLS = 512;
 // TMEM column map.  The pipeline moves UNITS of two tiles (the same 25-bar chunk for two individuals of the
 // group), so that every mbarrier round trip and every issuer iteration is shared by two tiles.  Three unit
@@ -73,14 +75,14 @@ struct Smem {
     uint8_t b1[GMAX][B1_BYTES];
     uint8_t b2[GMAX][B2_BYTES];
     uint8_t b3[GMAX][B3_BYTES];
-    double tab_r[2][GMAX][TAB_R_STRIDE];       // reward of (bar, inventory) rows
-    uint8_t tab_n[2][GMAX][TAB_N_STRIDE];      // next inventory index | traded << 3, 8 bytes per bar
+    double tab_r[3][GMAX][TAB_R_STRIDE];       // reward of (bar, inventory) rows; chunk q lives in buffer q % 3
+    uint8_t tab_n[3][GMAX][TAB_N_STRIDE];      // next inventory index | traded << 3, 8 bytes per bar
     uint64_t a1_full[A1_STAGES], a1_empty[A1_STAGES];
     // per TMEM buffer.  l*_done = tcgen05.commit of the layer's MMAs: its accumulator is complete AND the A
     // operand it read (which lives where the previous layer's accumulator was) may be overwritten.
     // a2_ready = E1 wrote A2 (4 warps); l3_ready = E2 wrote A3 (4) + E3 drained the previous D3 (4).
     uint64_t l1_done[3], a2_ready[3], l2_done[3], l3_ready[3], l3_done[3];
-    uint64_t tab_full[2], tab_empty[2];
+    uint64_t tab_full[3], tab_empty[3];
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -98,6 +100,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifdef SGMM_TC32_WATCHDOG
+// debug build: a wait that does not complete within ~1 s reports who waits on what and traps
+__device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 2000000000ll) {
+            if ((threadIdx.x & 31) == 0)
+                printf("tc32 watchdog: block %d warp %d waits on barrier +%u parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                       smem_u32(bar) & 0xFFFFu, parity);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -110,6 +131,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "LAB_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -286,14 +308,30 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// np.round(q).astype(int) (drl_engine.py:39): round-half-even.  For |q| < 2^22 the fp32 add of 1.5 * 2^23 rounds
+// exactly like cvt.rni and leaves the integer in the low mantissa bits (no trip through the conversion pipe);
+// larger magnitudes take the conversion instruction (saturating).
+__device__ __forceinline__ int quantise(float q)
+{
+    if (fabsf(q) < 4194304.0f) return __float_as_int(__fadd_rn(q, 12582912.0f)) - 0x4B400000;
+    return __float2int_rn(q);
+}
+// exact int32 -> fp64 without the conversion pipe: 2^52 + 2^31 + (k ^ 0x80000000) as a bit pattern, minus the bias
+__device__ __forceinline__ double int_to_double(int k)
+{
+    return __dadd_rn(__hiloint2double(0x43300000, k ^ (int)0x80000000), -4503601774854144.0);
+}
+
 // position of a unit in the pipeline: TMEM buffer (unit index mod 3) and mbarrier phase parity (use count & 1)
 struct Slot {
     uint32_t b, par, col;            // buffer, parity, TMEM column offset of the buffer (b * BUF_COLS)
     __device__ __forceinline__ void init(uint32_t i) { b = i % NBUF; par = (i / NBUF) & 1u; col = b * BUF_COLS; }
-    __device__ __forceinline__ void advance(uint32_t n)                                          // n <= NBUF
+    template <uint32_t N>
+    __device__ __forceinline__ void advance()                                                    // N <= 2 * NBUF
     {
-        b += n; col += n * BUF_COLS;
+        b += N; col += N * BUF_COLS;
         if (b >= NBUF) { b -= NBUF; col -= NBUF * BUF_COLS; par ^= 1u; }
+        if (N > NBUF) { if (b >= NBUF) { b -= NBUF; col -= NBUF * BUF_COLS; par ^= 1u; } }
     }
 };
 
@@ -343,7 +381,7 @@ __device__ __forceinline__ void issue_role(Smem& sm, uint32_t tmem_base, uint32_
             umma_commit(&done[sl.b]);
         }
         __syncwarp();
-        sl.advance(1);
+        sl.advance<1>();
         blo += 2 * BSTEP;
         if (++u == UG) { u = 0; blo = blo0; }
     }
@@ -351,14 +389,14 @@ __device__ __forceinline__ void issue_role(Smem& sm, uint32_t tmem_base, uint32_
 
 // E1 / E2: accumulator (fp32, TMEM) -> ReLU -> bf16 pairs written back IN PLACE as the next layer's A operand
 template <int LAYER>
-__device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint32_t gt, uint32_t it0, uint32_t nunits, int lane)
+__device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint32_t gt, uint32_t nunits, int lane)
 {
     uint64_t* done_in = LAYER == 1 ? sm.l1_done : sm.l2_done;        // accumulator complete
     uint64_t* filled = LAYER == 1 ? sm.a2_ready : sm.l3_ready;       // A operand written
     const uint32_t r_addr = lane_addr + (LAYER == 1 ? C_R1 : C_R2);
-    Slot sl; sl.init(gt + it0);
+    Slot sl; sl.init(gt);
 #pragma unroll 1
-    for (uint32_t it = it0; it < nunits; it += 2, sl.advance(2)) {
+    for (uint32_t it = 0; it < nunits; ++it, sl.advance<1>()) {
         const uint32_t addr = r_addr + sl.col;
         mbar_wait(&done_in[sl.b], sl.par);
         tc_fence_after();
@@ -399,7 +437,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
             mbar_init(&sm.l1_done[i], 1); mbar_init(&sm.a2_ready[i], 4);
             mbar_init(&sm.l2_done[i], 1); mbar_init(&sm.l3_ready[i], 8); mbar_init(&sm.l3_done[i], 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_L1) {
@@ -414,7 +452,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may touch (warp % 4)
-    const uint32_t pset = (uint32_t)(warp >> 2) & 1u;     // epilogue warps: even or odd units
+    const uint32_t e3set = (uint32_t)(warp - 8) >> 2;     // E3 warps: set s owns TMEM buffer s, i.e. the units with (global index % 3) == s
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     if (warp < 4) {
         // the constant K-step shared by every layer-2 / layer-3 MMA: K slots 32, 33 = 1.0 (they meet the
@@ -424,7 +462,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
         tmem_st_wait();
     }
     // "previous accumulator drained" half of the first use of the l3_ready barriers
-    if (warp >= 16 && warp < 20 && lane == 0) { for (int i = 0; i < NBUF; ++i) mbar_arrive(&sm.l3_ready[i]); }
+    if (warp >= 8 && warp < 12 && lane == 0) { for (int i = 0; i < NBUF; ++i) mbar_arrive(&sm.l3_ready[i]); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -460,14 +498,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        // first unit of this group that belongs to this warp's set (even / odd global unit index)
-        const uint32_t it0 = ((gt & 1u) == pset) ? 0u : 1u;
-
-        if (warp < 8) {
-            convert_role<1>(sm, lane_addr, gt, it0, nunits, lane);
-        } else if (warp < 16) {
-            convert_role<2>(sm, lane_addr, gt, it0, nunits, lane);
-        } else if (warp < 24) {
+        if (warp < 4) {
+            convert_role<1>(sm, lane_addr, gt, nunits, lane);
+        } else if (warp < 8) {
+            convert_role<2>(sm, lane_addr, gt, nunits, lane);
+        } else if (warp < 20) {
             // =========================== E3 : offsets, speculative env step, table ================
             const int row = quarter * 32 + lane;
             const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
@@ -484,25 +519,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                     m = __ldg(&a.px[t].mid_next);
                 }
             };
-            // this warp's units: it0, it0+2, ...; unit -> (chunk c, pair position up) tracked incrementally
+            // this set's units: it0, it0+3, ... (always TMEM buffer e3set, consecutive uses of its barriers, so
+            // every parity wait is at most one phase away); unit -> (chunk c, pair position up) incrementally
+            const uint32_t it0 = (e3set + NBUF - gt % NBUF) % NBUF;
             uint32_t c = it0 / UG, up = it0 - c * UG;
             bool fresh = true;                                                        // first unit of a chunk for this warp
             if (it0 < nunits) load_bar(c, kth_n, ab_n, mid_n);
             Slot sl; sl.init(gt + it0);
-            const uint32_t cstep = UG == 1 ? 2u : 1u;                                 // distance to the next chunk this warp sees
             double* const tab_r0 = &sm.tab_r[0][0][row];
             uint8_t* const tab_n0 = &sm.tab_n[0][0][tl * 8 + iv];
             const int inv = iv - 2;
 #pragma unroll 1
-            for (uint32_t it = it0; it < nunits; it += 2, sl.advance(2)) {
-                const uint32_t q = gc + c, cbuf = q & 1u;
+            for (uint32_t it = it0; it < nunits; it += NBUF, sl.par ^= 1u) {
+                const uint32_t q = gc + c, cbuf = q % 3u;
                 const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
+                // where this set's next unit lives; if it opens another chunk, fetch that chunk's bars now
+                uint32_t c2 = c, up2 = up + NBUF;
+                while (up2 >= UG) { up2 -= UG; ++c2; }
                 if (fresh) {
                     fresh = false;
                     kth = kth_n; ab = ab_n; mid = mid_n;
-                    if (c + cstep < nchunks) load_bar(c + cstep, kth_n, ab_n, mid_n);       // prefetch its bars
-                    mbar_wait(&sm.tab_empty[cbuf], ((q >> 1) & 1u) ^ 1u);                   // walker has left this table buffer
+                    mbar_wait(&sm.tab_empty[cbuf], ((q / 3u) & 1u) ^ 1u);                   // walker has left this table buffer
                 }
+                if (c2 != c && c2 < nchunks) load_bar(c2, kth_n, ab_n, mid_n);
                 mbar_wait(&sm.l3_done[sl.b], sl.par);
                 tc_fence_after();
                 uint32_t v[2][4];
@@ -514,43 +553,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 if (lane == 0) mbar_arrive(&sm.l3_ready[sl.b]);                              // accumulator drained
                 double* tr = tab_r0 + (cbuf * GMAX + up * 2u) * TAB_R_STRIDE;
                 uint8_t* tn = tab_n0 + (cbuf * GMAX + up * 2u) * TAB_N_STRIDE;
+                // Both tiles of the unit, branch-free so that the two dependency chains interleave.  Rows that
+                // are not valid compute on stale bar data and store nothing.
+                float ra[2], rb[2]; double rew[2]; uint32_t nxt[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const float ra = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));      // hi + lo halves of W3
-                    const float rb = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
-                    const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));                            // drl_engine.py:39
-                    const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
-                    if (valid) {
-                        // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                        const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
-                        const bool fs = (inv > -2) && (ka < kth.x);              // :35,:38
-                        const double my_ask = add_rn(ab.x, mul_rn((double)ka, a.tick));
-                        const double my_bid = sub_rn(ab.y, mul_rn((double)kb, a.tick));
-                        double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
-                        if (FEE) {
-                            leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
-                            leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
-                        }
-                        double pnl = 0.0;
-                        pnl = fb ? add_rn(pnl, leg_b) : pnl;
-                        pnl = fs ? add_rn(pnl, leg_s) : pnl;
-                        const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
-                        const int ai = ninv < 0 ? -ninv : ninv;
-                        tr[j * TAB_R_STRIDE] = sub_rn(pnl, mul_rn(a.phi, (double)ai));             // :57-58
-                        tn[j * TAB_N_STRIDE] = (uint8_t)((ninv + 2) | ((fb || fs) ? 8 : 0));
-                        if (a.raw_table) {
+                    ra[j] = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));       // hi + lo halves of W3
+                    rb[j] = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
+                    const int ka = quantise(__fmul_rn(ra[j], 5.0f));                             // drl_engine.py:39
+                    const int kb = quantise(__fmul_rn(rb[j], 5.0f));
+                    // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
+                    const bool fb = (inv < 2) && (kb < kth.y);                   // :34,:37
+                    const bool fs = (inv > -2) && (ka < kth.x);                  // :35,:38
+                    const double my_ask = add_rn(ab.x, mul_rn(int_to_double(ka), a.tick));
+                    const double my_bid = sub_rn(ab.y, mul_rn(int_to_double(kb), a.tick));
+                    double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
+                    if (FEE) {
+                        leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
+                        leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
+                    }
+                    double pnl = 0.0;
+                    pnl = fb ? add_rn(pnl, leg_b) : pnl;
+                    pnl = fs ? add_rn(pnl, leg_s) : pnl;
+                    const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
+                    const double pen = mul_rn(a.phi, int_to_double(ninv < 0 ? -ninv : ninv));          // phi * |inv'|  (:57)
+                    rew[j] = sub_rn(pnl, pen);                                                         // :58
+                    nxt[j] = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        tr[j * TAB_R_STRIDE] = rew[j];
+                        tn[j * TAB_N_STRIDE] = (uint8_t)nxt[j];
+                    }
+                    if (a.raw_table) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
                             const int64_t ind = grp * G + (int64_t)(up * 2u) + j;
                             if (ind < pop.count) {
                                 float* o = a.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
-                                __stcg(o, ra); __stcg(o + 1, rb);
+                                __stcg(o, ra[j]); __stcg(o + 1, rb[j]);
                             }
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.tab_full[cbuf]);
-                up += 2;
-                while (up >= UG) { up -= UG; ++c; fresh = true; }        // (UG == 1: two chunks ahead)
+                fresh = c2 != c;
+                c = c2; up = up2;
             }
         } else if (warp == WARP_L1) {
             // =========================== L1 ISSUER + A1 TMA PRODUCER ===============================
@@ -588,7 +638,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                     if (last) umma_commit(&sm.a1_empty[slot]);
                 }
                 __syncwarp();
-                sl.advance(1);
+                sl.advance<1>();
                 blo += 2u * (uint32_t)(B1_BYTES >> 4);
                 if (last) { u1 = 0; ++c1; blo = b1lo0; } else ++u1;
             }
@@ -605,27 +655,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
             double total = 0.0;                                           // drl_engine.py:26
 #pragma unroll 1
             for (uint32_t c = 0; c < nchunks; ++c) {
-                const uint32_t q = gc + c, cbuf = q & 1u, cpar = (q >> 1) & 1u;
+                const uint32_t q = gc + c, cbuf = q % 3u, cpar = (q / 3u) & 1u;
                 mbar_wait(&sm.tab_full[cbuf], cpar);
                 if (live) {
                     const int64_t t0 = (int64_t)c * TILE_BARS;
                     const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
                     const uint8_t* nb = sm.tab_n[cbuf][g];
                     const double* rb = sm.tab_r[cbuf][g];
+                    // phase A: the 5-state automaton alone (integer chain); remember the visited inventory of each bar
+                    uint32_t ivs[TILE_BARS];
+#pragma unroll
+                    for (int s = 0; s < TILE_BARS; ++s) {
+                        ivs[s] = (uint32_t)iv;
+                        if (s < n) {
+                            const uint2 w = *reinterpret_cast<const uint2*>(nb + s * 8);
+                            const uint32_t e = __byte_perm(w.x, w.y, (uint32_t)iv);
+                            trades += (int)((e >> 3) & 1u);                       // drl_engine.py:60-61
+                            iv = (int)(e & 7u);
+                        }
+                    }
+                    // phase B: rewards of the visited rows, summed in the reference's order (drl_engine.py:54)
 #pragma unroll
                     for (int s = 0; s < TILE_BARS; ++s) {
                         if (s < n) {
-                            const uint2 w = *reinterpret_cast<const uint2*>(nb + s * 8);
-                            const uint32_t e = __byte_perm(w.x, w.y, (uint32_t)iv) & 0xFFu;
-                            total = add_rn(total, rb[s * 5 + iv]);                // drl_engine.py:54
-                            trades += (int)(e >> 3);                              // :60-61
+                            total = add_rn(total, rb[s * 5 + ivs[s]]);
                             if (a.act_trace) {
-                                const float* o = a.raw_table + (((int64_t)ind * T + t0 + s) * 5 + iv) * 2;
+                                const float* o = a.raw_table + (((int64_t)ind * T + t0 + s) * 5 + ivs[s]) * 2;
                                 int32_t* at = a.act_trace + ((int64_t)ind * T + t0 + s) * 2;
-                                at[0] = __float2int_rn(__fmul_rn(__ldcg(o), 5.0f));
-                                at[1] = __float2int_rn(__fmul_rn(__ldcg(o + 1), 5.0f));
+                                at[0] = quantise(__fmul_rn(__ldcg(o), 5.0f));
+                                at[1] = quantise(__fmul_rn(__ldcg(o + 1), 5.0f));
                             }
-                            iv = (int)(e & 7u);
                         }
                     }
                 }
