@@ -322,6 +322,36 @@ __device__ __forceinline__ double int_to_double(int k)
     return __dadd_rn(__hiloint2double(0x43300000, k ^ (int)0x80000000), -4503601774854144.0);
 }
 
+// One 25-bar chunk of one individual's walk through the table.
+//   phase A: the 5-state automaton alone (a 2-instruction integer chain per bar), remembering the inventory
+//            each bar was entered with;
+//   phase B: rewards of the visited rows, summed in the reference's order (drl_engine.py:54); their loads do
+//            not depend on the running sum, so only the fp64 add chain is serial.
+// FULL = all 25 bars present (no per-bar predicates).
+template <bool FULL>
+__device__ __forceinline__ void walk_chunk(const uint8_t* nb, const double* rb, int n, int& iv, int& trades, double& total)
+{
+    uint32_t es[TILE_BARS], ivs[TILE_BARS];
+    uint32_t w = (uint32_t)iv;
+#pragma unroll
+    for (int s = 0; s < TILE_BARS; ++s) {
+        ivs[s] = w; es[s] = 0;
+        if (FULL || s < n) {
+            const uint2 x = *reinterpret_cast<const uint2*>(nb + s * 8);
+            es[s] = __byte_perm(x.x, x.y, w);          // byte `w` of the bar's 8-byte record: next | traded << 3
+            w = es[s] & 7u;
+        }
+    }
+    iv = (int)w;
+#pragma unroll
+    for (int s = 0; s < TILE_BARS; ++s) {
+        if (FULL || s < n) {
+            trades += (int)((es[s] >> 3) & 1u);                                   // drl_engine.py:60-61
+            total = add_rn(total, rb[s * 5 + ivs[s]]);
+        }
+    }
+}
+
 // position of a unit in the pipeline: TMEM buffer (unit index mod 3) and mbarrier phase parity (use count & 1)
 struct Slot {
     uint32_t b, par, col;            // buffer, parity, TMEM column offset of the buffer (b * BUF_COLS)
@@ -662,28 +692,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                     const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
                     const uint8_t* nb = sm.tab_n[cbuf][g];
                     const double* rb = sm.tab_r[cbuf][g];
-                    // phase A: the 5-state automaton alone (integer chain); remember the visited inventory of each bar
-                    uint32_t ivs[TILE_BARS];
-#pragma unroll
-                    for (int s = 0; s < TILE_BARS; ++s) {
-                        ivs[s] = (uint32_t)iv;
-                        if (s < n) {
-                            const uint2 w = *reinterpret_cast<const uint2*>(nb + s * 8);
-                            const uint32_t e = __byte_perm(w.x, w.y, (uint32_t)iv);
-                            trades += (int)((e >> 3) & 1u);                       // drl_engine.py:60-61
-                            iv = (int)(e & 7u);
-                        }
-                    }
-                    // phase B: rewards of the visited rows, summed in the reference's order (drl_engine.py:54)
-#pragma unroll
-                    for (int s = 0; s < TILE_BARS; ++s) {
-                        if (s < n) {
-                            total = add_rn(total, rb[s * 5 + ivs[s]]);
-                            if (a.act_trace) {
-                                const float* o = a.raw_table + (((int64_t)ind * T + t0 + s) * 5 + ivs[s]) * 2;
+                    if (n == TILE_BARS && !a.act_trace) walk_chunk<true>(nb, rb, n, iv, trades, total);      // every chunk but the last
+                    else {
+                        const int iv0 = iv;
+                        walk_chunk<false>(nb, rb, n, iv, trades, total);
+                        if (a.act_trace) {                                    // audit: the offsets taken (second pass over the automaton)
+                            int w = iv0;
+                            for (int s = 0; s < n; ++s) {
+                                const float* o = a.raw_table + (((int64_t)ind * T + t0 + s) * 5 + w) * 2;
                                 int32_t* at = a.act_trace + ((int64_t)ind * T + t0 + s) * 2;
                                 at[0] = quantise(__fmul_rn(__ldcg(o), 5.0f));
                                 at[1] = quantise(__fmul_rn(__ldcg(o + 1), 5.0f));
+                                w = nb[s * 8 + w] & 7;
                             }
                         }
                     }
