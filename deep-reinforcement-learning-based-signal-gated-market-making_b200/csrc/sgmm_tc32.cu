@@ -430,17 +430,17 @@ __device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint3
         const uint32_t addr = r_addr + sl.col;
         mbar_wait(&done_in[sl.b], sl.par);
         tc_fence_after();
-        uint32_t v[32], p[16];
-        tmem_ld32(addr, v);
+        uint32_t v0[32], v1[32];
+        tmem_ld32(addr, v0);
+        tmem_ld32(addr + S_D, v1);                                   // second tile of the unit
         tmem_ld_wait();
+        uint32_t p0[16], p1[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        tmem_ld32(addr + S_D, v);                                    // second tile of the unit
-        tmem_st16(addr, p);
-        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) p0[j] = pack_relu_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+        tmem_st16(addr, p0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        tmem_st16(addr + S_D, p);
+        for (int j = 0; j < 16; ++j) p1[j] = pack_relu_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+        tmem_st16(addr + S_D, p1);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -549,88 +549,87 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                     m = __ldg(&a.px[t].mid_next);
                 }
             };
-            // this set's units: it0, it0+3, ... (always TMEM buffer e3set, consecutive uses of its barriers, so
-            // every parity wait is at most one phase away); unit -> (chunk c, pair position up) incrementally
-            const uint32_t it0 = (e3set + NBUF - gt % NBUF) % NBUF;
-            uint32_t c = it0 / UG, up = it0 - c * UG;
-            bool fresh = true;                                                        // first unit of a chunk for this warp
-            if (it0 < nunits) load_bar(c, kth_n, ab_n, mid_n);
-            Slot sl; sl.init(gt + it0);
-            double* const tab_r0 = &sm.tab_r[0][0][row];
-            uint8_t* const tab_n0 = &sm.tab_n[0][0][tl * 8 + iv];
+            // This set's units are those with (global unit index % 3) == e3set: always TMEM buffer e3set and
+            // consecutive uses of its barriers, so every parity wait is at most one phase away.
+            // Outer loop over chunks (bar data, table buffer), inner loop over the set's units of the chunk.
+            const uint32_t taddr = d_addr + e3set * BUF_COLS;
+            uint64_t* const l3_done = &sm.l3_done[e3set];
+            uint64_t* const l3_ready = &sm.l3_ready[e3set];
+            uint32_t par = ((gt + (e3set + NBUF - gt % NBUF) % NBUF) / NBUF) & 1u;       // parity of this set's first unit
+            uint32_t base3 = gt % NBUF;                                                 // (global index of the chunk's first unit) % 3
+            const uint32_t ug3 = UG % NBUF;
             const int inv = iv - 2;
+            if (nchunks > 0) load_bar(0, kth_n, ab_n, mid_n);
 #pragma unroll 1
-            for (uint32_t it = it0; it < nunits; it += NBUF, sl.par ^= 1u) {
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                kth = kth_n; ab = ab_n; mid = mid_n;
+                if (c + 1 < nchunks) load_bar(c + 1, kth_n, ab_n, mid_n);               // prefetch the next chunk's bars
+                uint32_t up = e3set >= base3 ? e3set - base3 : e3set + NBUF - base3;    // first unit of the chunk that is ours
+                base3 += ug3; if (base3 >= NBUF) base3 -= NBUF;
+                if (up >= UG) continue;                                                 // (groups of 2 or 4: not every chunk has one)
                 const uint32_t q = gc + c, cbuf = q % 3u;
                 const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
-                // where this set's next unit lives; if it opens another chunk, fetch that chunk's bars now
-                uint32_t c2 = c, up2 = up + NBUF;
-                while (up2 >= UG) { up2 -= UG; ++c2; }
-                if (fresh) {
-                    fresh = false;
-                    kth = kth_n; ab = ab_n; mid = mid_n;
-                    mbar_wait(&sm.tab_empty[cbuf], ((q / 3u) & 1u) ^ 1u);                   // walker has left this table buffer
-                }
-                if (c2 != c && c2 < nchunks) load_bar(c2, kth_n, ab_n, mid_n);
-                mbar_wait(&sm.l3_done[sl.b], sl.par);
-                tc_fence_after();
-                uint32_t v[2][4];
-                tmem_ld4(d_addr + sl.col, v[0]);
-                tmem_ld4(d_addr + sl.col + S_D3, v[1]);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.l3_ready[sl.b]);                              // accumulator drained
-                double* tr = tab_r0 + (cbuf * GMAX + up * 2u) * TAB_R_STRIDE;
-                uint8_t* tn = tab_n0 + (cbuf * GMAX + up * 2u) * TAB_N_STRIDE;
-                // Both tiles of the unit, branch-free so that the two dependency chains interleave.  Rows that
-                // are not valid compute on stale bar data and store nothing.
-                float ra[2], rb[2]; double rew[2]; uint32_t nxt[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    ra[j] = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));       // hi + lo halves of W3
-                    rb[j] = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
-                    const int ka = quantise(__fmul_rn(ra[j], 5.0f));                             // drl_engine.py:39
-                    const int kb = quantise(__fmul_rn(rb[j], 5.0f));
-                    // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                    const bool fb = (inv < 2) && (kb < kth.y);                   // :34,:37
-                    const bool fs = (inv > -2) && (ka < kth.x);                  // :35,:38
-                    const double my_ask = add_rn(ab.x, mul_rn(int_to_double(ka), a.tick));
-                    const double my_bid = sub_rn(ab.y, mul_rn(int_to_double(kb), a.tick));
-                    double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
-                    if (FEE) {
-                        leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
-                        leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
-                    }
-                    double pnl = 0.0;
-                    pnl = fb ? add_rn(pnl, leg_b) : pnl;
-                    pnl = fs ? add_rn(pnl, leg_s) : pnl;
-                    const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
-                    const double pen = mul_rn(a.phi, int_to_double(ninv < 0 ? -ninv : ninv));          // phi * |inv'|  (:57)
-                    rew[j] = sub_rn(pnl, pen);                                                         // :58
-                    nxt[j] = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
-                }
-                if (valid) {
+                mbar_wait(&sm.tab_empty[cbuf], ((q / 3u) & 1u) ^ 1u);                   // walker has left this table buffer
+                double* tr = &sm.tab_r[cbuf][up * 2u][row];
+                uint8_t* tn = &sm.tab_n[cbuf][up * 2u][tl * 8 + iv];
+#pragma unroll 1
+                for (; up < UG; up += NBUF, par ^= 1u, tr += 2 * NBUF * TAB_R_STRIDE, tn += 2 * NBUF * TAB_N_STRIDE) {
+                    mbar_wait(l3_done, par);
+                    tc_fence_after();
+                    uint32_t v[2][4];
+                    tmem_ld4(taddr, v[0]);
+                    tmem_ld4(taddr + S_D3, v[1]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(l3_ready);                                // accumulator drained
+                    // Both tiles of the unit, branch-free so that the two dependency chains interleave.  Rows that
+                    // are not valid compute on stale bar data and store nothing.
+                    float ra[2], rb[2]; double rew[2]; uint32_t nxt[2];
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        tr[j * TAB_R_STRIDE] = rew[j];
-                        tn[j * TAB_N_STRIDE] = (uint8_t)nxt[j];
+                        ra[j] = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));       // hi + lo halves of W3
+                        rb[j] = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
+                        const int ka = quantise(__fmul_rn(ra[j], 5.0f));                             // drl_engine.py:39
+                        const int kb = quantise(__fmul_rn(rb[j], 5.0f));
+                        // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
+                        const bool fb = (inv < 2) && (kb < kth.y);                   // :34,:37
+                        const bool fs = (inv > -2) && (ka < kth.x);                  // :35,:38
+                        const double my_ask = add_rn(ab.x, mul_rn(int_to_double(ka), a.tick));
+                        const double my_bid = sub_rn(ab.y, mul_rn(int_to_double(kb), a.tick));
+                        double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
+                        if (FEE) {
+                            leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
+                            leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
+                        }
+                        double pnl = 0.0;
+                        pnl = fb ? add_rn(pnl, leg_b) : pnl;
+                        pnl = fs ? add_rn(pnl, leg_s) : pnl;
+                        const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
+                        const double pen = mul_rn(a.phi, int_to_double(ninv < 0 ? -ninv : ninv));          // phi * |inv'|  (:57)
+                        rew[j] = sub_rn(pnl, pen);                                                         // :58
+                        nxt[j] = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
                     }
-                    if (a.raw_table) {
+                    if (valid) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const int64_t ind = grp * G + (int64_t)(up * 2u) + j;
-                            if (ind < pop.count) {
-                                float* o = a.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
-                                __stcg(o, ra[j]); __stcg(o + 1, rb[j]);
+                            tr[j * TAB_R_STRIDE] = rew[j];
+                            tn[j * TAB_N_STRIDE] = (uint8_t)nxt[j];
+                        }
+                        if (a.raw_table) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int64_t ind = grp * G + (int64_t)(up * 2u) + j;
+                                if (ind < pop.count) {
+                                    float* o = a.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
+                                    __stcg(o, ra[j]); __stcg(o + 1, rb[j]);
+                                }
                             }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.tab_full[cbuf]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tab_full[cbuf]);
-                fresh = c2 != c;
-                c = c2; up = up2;
             }
         } else if (warp == WARP_L1) {
             // =========================== L1 ISSUER + A1 TMA PRODUCER ===============================
