@@ -20,13 +20,13 @@
 // One persistent CTA per SM works on a GROUP of up to 16 individuals in lockstep over time: the A1 tile
 // of a 25-bar chunk is loaded once and multiplied with every individual's weights (a grouped GEMM:
 // per-individual B operands, shared A operand), 16 walker lanes advance 16 independent automata.
-//   warps 0-3   E1 : D1 -> relu -> bf16 -> A2 (in place)      (warp % 4 = TMEM lane quarter)
-//   warps 4-7   E2 : D2 -> relu -> bf16 -> A3 (in place)
-//   warps 8-19  E3 : D3 -> offsets -> speculative env step -> table; three sets of four warps, set s owns
+//   warps 0-11  E12: three sets of four warps (warp % 4 = TMEM lane quarter), set s owns TMEM buffer s: for each
+//                    of its units D1 -> relu -> bf16 -> A2 (in place), then D2 -> relu -> bf16 -> A3 (in place)
+//   warps 12-23 E3 : D3 -> offsets -> speculative env step -> table; three sets of four warps, set s owns
 //                    TMEM buffer s (the fp64 step is a long dependency chain: latency, not issue slots)
-//   warps 20-22 L1 / L2 / L3 issuers: a converged warp each, one elected lane issues tcgen05.mma + commit
+//   warps 24-26 L1 / L2 / L3 issuers: a converged warp each, one elected lane issues tcgen05.mma + commit
 //               (three independent issue streams; the L1 warp also feeds the A1 ring with TMA bulk copies)
-//   warp  23    walker
+//   warp  27    walker
 // Every TMEM region is double-buffered; per layer and buffer one "ready" mbarrier (A written + D drained)
 // and one "done" mbarrier (tcgen05.commit).
 //
@@ -53,8 +53,8 @@ constexpr int B1_BYTES = H * K1 * 2;           // 1024
 constexpr int B2_BYTES = H * K2 * 2;           // 3072
 constexpr int B3_BYTES = 16 * K2 * 2;          // 1536
 constexpr int A1_STAGES = 4;
-constexpr int WARP_L1 = 20, WARP_L2 = 21, WARP_L3 = 22;     // warp 23 = walker
-constexpr int NUM_THREADS = 768;
+constexpr int WARP_E3 = 12, WARP_L1 = 24, WARP_L2 = 25, WARP_L3 = 26;     // warp 27 = walker
+constexpr int NUM_THREADS = 896;
 constexpr uint32_t TMEM_COLS = 512;
 // TMEM column map.  The pipeline moves UNITS of two tiles (the same 25-bar chunk for two individuals of the
 // group), so that every mbarrier round trip and every issuer iteration is shared by two tiles.  Three unit
@@ -346,7 +346,7 @@ __device__ __forceinline__ void walk_chunk(const uint8_t* nb, const double* rb, 
 #pragma unroll
     for (int s = 0; s < TILE_BARS; ++s) {
         if (FULL || s < n) {
-            trades += (int)((es[s] >> 3) & 1u);                                   // drl_engine.py:60-61
+            trades += (int)(es[s] & 8u);                                          // drl_engine.py:60-61 (x8; divided out by the caller)
             total = add_rn(total, rb[s * 5 + ivs[s]]);
         }
     }
@@ -417,34 +417,47 @@ __device__ __forceinline__ void issue_role(Smem& sm, uint32_t tmem_base, uint32_
     }
 }
 
-// E1 / E2: accumulator (fp32, TMEM) -> ReLU -> bf16 pairs written back IN PLACE as the next layer's A operand
-template <int LAYER>
-__device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint32_t gt, uint32_t nunits, int lane)
+// accumulator (fp32, TMEM) -> ReLU -> bf16 pairs written back IN PLACE as the next layer's A operand, both tiles
+// of a unit, this warp's 32 rows
+__device__ __forceinline__ void convert_unit(uint32_t addr)
 {
-    uint64_t* done_in = LAYER == 1 ? sm.l1_done : sm.l2_done;        // accumulator complete
-    uint64_t* filled = LAYER == 1 ? sm.a2_ready : sm.l3_ready;       // A operand written
-    const uint32_t r_addr = lane_addr + (LAYER == 1 ? C_R1 : C_R2);
-    Slot sl; sl.init(gt);
+    uint32_t v[32], p[16];
+    tmem_ld32(addr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    tmem_ld32(addr + S_D, v);                                        // second tile of the unit
+    tmem_st16(addr, p);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    tmem_st16(addr + S_D, p);
+    tmem_st_wait();
+    tc_fence_before();
+}
+
+// E12: set s (four warps) owns TMEM buffer s: for each of its units it converts D1 -> A2, then D2 -> A3
+__device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint32_t set, uint32_t gt, uint32_t nunits, int lane)
+{
+    const uint32_t it0 = (set + NBUF - gt % NBUF) % NBUF;
+    uint32_t par = ((gt + it0) / NBUF) & 1u;
+    const uint32_t r1 = lane_addr + C_R1 + set * BUF_COLS, r2 = lane_addr + C_R2 + set * BUF_COLS;
+    uint64_t* const l1_done = &sm.l1_done[set];
+    uint64_t* const a2_ready = &sm.a2_ready[set];
+    uint64_t* const l2_done = &sm.l2_done[set];
+    uint64_t* const l3_ready = &sm.l3_ready[set];
 #pragma unroll 1
-    for (uint32_t it = 0; it < nunits; ++it, sl.advance<1>()) {
-        const uint32_t addr = r_addr + sl.col;
-        mbar_wait(&done_in[sl.b], sl.par);
+    for (uint32_t it = it0; it < nunits; it += NBUF, par ^= 1u) {
+        mbar_wait(l1_done, par);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld32(addr, v0);
-        tmem_ld32(addr + S_D, v1);                                   // second tile of the unit
-        tmem_ld_wait();
-        uint32_t p0[16], p1[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) p0[j] = pack_relu_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
-        tmem_st16(addr, p0);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) p1[j] = pack_relu_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
-        tmem_st16(addr + S_D, p1);
-        tmem_st_wait();
-        tc_fence_before();
+        convert_unit(r1);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&filled[sl.b]);
+        if (lane == 0) mbar_arrive(a2_ready);
+        mbar_wait(l2_done, par);
+        tc_fence_after();
+        convert_unit(r2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(l3_ready);
     }
 }
 
@@ -482,7 +495,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may touch (warp % 4)
-    const uint32_t e3set = (uint32_t)(warp - 8) >> 2;     // E3 warps: set s owns TMEM buffer s, i.e. the units with (global index % 3) == s
+    const uint32_t e3set = (uint32_t)(warp - WARP_E3) >> 2;     // E3 warps: set s owns TMEM buffer s, i.e. the units with (global index % 3) == s
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     if (warp < 4) {
         // the constant K-step shared by every layer-2 / layer-3 MMA: K slots 32, 33 = 1.0 (they meet the
@@ -492,7 +505,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
         tmem_st_wait();
     }
     // "previous accumulator drained" half of the first use of the l3_ready barriers
-    if (warp >= 8 && warp < 12 && lane == 0) { for (int i = 0; i < NBUF; ++i) mbar_arrive(&sm.l3_ready[i]); }
+    if (warp >= WARP_E3 && warp < WARP_L1 && lane == 0) mbar_arrive(&sm.l3_ready[e3set]);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -528,11 +541,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        if (warp < 4) {
-            convert_role<1>(sm, lane_addr, gt, nunits, lane);
-        } else if (warp < 8) {
-            convert_role<2>(sm, lane_addr, gt, nunits, lane);
-        } else if (warp < 20) {
+        if (warp < WARP_E3) {
+            convert_role(sm, lane_addr, (uint32_t)warp >> 2, gt, nunits, lane);
+        } else if (warp < WARP_L1) {
             // =========================== E3 : offsets, speculative env step, table ================
             const int row = quarter * 32 + lane;
             const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
@@ -711,6 +722,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 if (lane == 0) mbar_arrive(&sm.tab_empty[cbuf]);
             }
             if (live) {
+                trades >>= 3;                                                  // walk_chunk counts in units of 8
                 if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
                 a.fitness[ind] = total; a.trades[ind] = trades;
             }
