@@ -381,39 +381,141 @@ __device__ __forceinline__ void umma_ss2(uint32_t d, uint32_t a_lo, uint32_t a_h
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }     // version 1 at bit 46
 
+// ---------------------------------------------------------------------------------------------
+// The warp roles.  Each is its own (non-inlined) function so that it gets its own register allocation and
+// loop optimisation; everything a role needs travels in one context record.
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    Smem* sm; uint32_t sm_addr;          // generic and shared-window address of the CTA's Smem
+    uint32_t tmem_base, lane_addr;       // TMEM base; base + this warp's lane quarter
+    uint32_t gt, gc;                     // units / chunks this CTA has processed before this group (phase sources)
+    uint32_t nchunks, UG, nunits;        // this group: chunks, units per chunk, units
+    int G, lane, quarter;
+    int64_t grp, T, count;
+    const BarSig* sig; const BarPx* px; const uint8_t* a1;
+    double tick, phi, fee;
+    double* fitness; int32_t* trades; float* raw_table; int32_t* act_trace;
+};
+
+#define BAR(member, idx) (cx.sm_addr + (uint32_t)offsetof(Smem, member) + (uint32_t)(idx) * 8u)
+
+__device__ __forceinline__ void mbar_wait_a_(const Ctx& cx, uint32_t addr, uint32_t parity)
+{
+#ifdef SGMM_TC32_WATCHDOG
+    // debug build: a wait that spins ~2^26 times reports who waits on what and traps
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1u << 22)) {
+            if ((threadIdx.x & 31) == 0)
+                printf("tc32 watchdog: block %d warp %d waits on barrier +0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), addr - BAR(a1_full, 0), parity);
+            __trap();
+        }
+    }
+#else
+    // (a plain loop around one try_wait; the form with a label and a branch inside the asm statement hung the
+    //  FEE instantiation of the kernel on the device although its SASS looked equivalent)
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t addr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+
 // L2 / L3 issuer: a converged warp; one elected lane issues the six MMAs of a unit and one commit
 template <int LAYER>
-__device__ __forceinline__ void issue_role(Smem& sm, uint32_t tmem_base, uint32_t gt, uint32_t nunits, uint32_t UG)
+__device__ __noinline__ void issue_role(const Ctx& cx)
 {
     constexpr uint32_t ID = LAYER == 2 ? idesc(32) : idesc(16);
     constexpr uint32_t DSTEP = LAYER == 2 ? S_D : S_D3;
     constexpr uint32_t BSTEP = (uint32_t)((LAYER == 2 ? B2_BYTES : B3_BYTES) >> 4);
-    uint64_t* ready = LAYER == 2 ? sm.a2_ready : sm.l3_ready;     // A operand written (L3: and previous D3 drained)
-    uint64_t* done = LAYER == 2 ? sm.l2_done : sm.l3_done;
-    const uint32_t d0 = tmem_base + (LAYER == 2 ? C_R2 : C_R3), a0 = tmem_base + (LAYER == 2 ? C_R1 : C_R2);
-    const uint32_t one = tmem_base + C_ONE;
-    const uint32_t blo0 = desc_lo(LAYER == 2 ? smem_u32(sm.b2[0]) : smem_u32(sm.b3[0]), 128), bhi = desc_hi(768);
+    const uint32_t ready0 = LAYER == 2 ? BAR(a2_ready, 0) : BAR(l3_ready, 0);     // A operand written (L3: and previous D3 drained)
+    const uint32_t done0 = LAYER == 2 ? BAR(l2_done, 0) : BAR(l3_done, 0);
+    const uint32_t l3done0 = BAR(l3_done, 0);
+    const uint32_t d0 = cx.tmem_base + (LAYER == 2 ? C_R2 : C_R3), a0 = cx.tmem_base + (LAYER == 2 ? C_R1 : C_R2);
+    const uint32_t one = cx.tmem_base + C_ONE;
+    const uint32_t blo0 = desc_lo(cx.sm_addr + (uint32_t)(LAYER == 2 ? offsetof(Smem, b2) : offsetof(Smem, b3)), 128), bhi = desc_hi(768);
+    const uint32_t UG = cx.UG, nunits = cx.nunits;
     uint32_t u = 0, blo = blo0;
-    Slot sl; sl.init(gt);
+    uint32_t b = cx.gt % NBUF, par = (cx.gt / NBUF) & 1u, col = b * BUF_COLS, boff = b * 8u;
 #pragma unroll 1
     for (uint32_t it = 0; it < nunits; ++it) {
-        mbar_wait(&ready[sl.b], sl.par);
-        if (LAYER == 2) mbar_wait(&sm.l3_done[sl.b], sl.par ^ 1u);    // layer 3 has read the A operand that lives where D2 goes
+        mbar_wait_a_(cx, ready0 + boff, par);
+        if (LAYER == 2) mbar_wait_a_(cx, l3done0 + boff, par ^ 1u);        // layer 3 has read the A operand that lives where D2 goes
         tc_fence_after();
         if (elect_one()) {
-            const uint32_t d = d0 + sl.col, aa = a0 + sl.col;
+            const uint32_t d = d0 + col, aa = a0 + col;
             umma_ts2(d, aa, blo, bhi, ID, 0u);
             umma_ts2(d, aa + 8, blo + 16, bhi, ID, 1u);                       // +256 B per K=16 step
             umma_ts2(d, one, blo + 32, bhi, ID, 1u);                          // bias step: A = the constant [1 1 0 ...] columns
             umma_ts2(d + DSTEP, aa + S_D, blo + BSTEP, bhi, ID, 0u);          // second tile of the unit
             umma_ts2(d + DSTEP, aa + S_D + 8, blo + BSTEP + 16, bhi, ID, 1u);
             umma_ts2(d + DSTEP, one, blo + BSTEP + 32, bhi, ID, 1u);
-            umma_commit(&done[sl.b]);
+            umma_commit_a(done0 + boff);
         }
         __syncwarp();
-        sl.advance<1>();
+        b += 1; col += BUF_COLS; boff += 8u;
+        if (b == NBUF) { b = 0; col = 0; boff = 0; par ^= 1u; }
         blo += 2 * BSTEP;
         if (++u == UG) { u = 0; blo = blo0; }
+    }
+}
+
+// L1 issuer + TMA producer of the A1 ring.  Both tiles of a unit share the A1 tile and their B1 operands are
+// adjacent in shared memory (4 row groups of 256 B each): ONE M=128, N=64, K=16 MMA fills D1 of both tiles.
+__device__ __noinline__ void l1_role(const Ctx& cx)
+{
+    const uint32_t nchunks = cx.nchunks, UG = cx.UG, nunits = cx.nunits, gc = cx.gc;
+    const uint32_t a1_smem = cx.sm_addr + (uint32_t)offsetof(Smem, a1);
+    auto load_a1 = [&](uint32_t c) {
+        const uint32_t q = gc + c, slot = q % A1_STAGES, use = q / A1_STAGES;
+        mbar_wait_a_(cx, BAR(a1_empty, slot), (use & 1u) ^ 1u);
+        if (elect_one()) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(BAR(a1_full, slot)), "r"((uint32_t)A1_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(a1_smem + slot * (uint32_t)A1_BYTES), "l"(cx.a1 + (size_t)c * A1_BYTES), "r"((uint32_t)A1_BYTES), "r"(BAR(a1_full, slot)) : "memory");
+        }
+        __syncwarp();
+    };
+    for (uint32_t c = 0; c < nchunks && c < (uint32_t)(A1_STAGES - 1); ++c) load_a1(c);
+    constexpr uint32_t ID64 = idesc(64);
+    const uint32_t b1lo0 = desc_lo(cx.sm_addr + (uint32_t)offsetof(Smem, b1), 128), dhi = desc_hi(256);
+    const uint32_t l2done0 = BAR(l2_done, 0), l1done0 = BAR(l1_done, 0);
+    uint32_t c1 = 0, u1 = 0, blo = b1lo0, alo = 0;
+    uint32_t b = cx.gt % NBUF, par = (cx.gt / NBUF) & 1u, col = b * BUF_COLS, boff = b * 8u;
+#pragma unroll 1
+    for (uint32_t it = 0; it < nunits; ++it) {
+        const uint32_t q = gc + c1, slot = q % A1_STAGES;
+        if (u1 == 0) {
+            if (c1 + A1_STAGES - 1 < nchunks) load_a1(c1 + A1_STAGES - 1);
+            mbar_wait_a_(cx, BAR(a1_full, slot), (q / A1_STAGES) & 1u);
+            alo = desc_lo(a1_smem + slot * (uint32_t)A1_BYTES, 128);
+        }
+        mbar_wait_a_(cx, l2done0 + boff, par ^ 1u);                // layer 2 of the unit that used this buffer before has read its A operand
+        tc_fence_after();
+        const bool last = (u1 + 1 == UG);
+        if (elect_one()) {
+            umma_ss2(cx.tmem_base + C_R1 + col, alo, dhi, blo, dhi, ID64, 0u);
+            umma_commit_a(l1done0 + boff);
+            if (last) umma_commit_a(BAR(a1_empty, slot));
+        }
+        __syncwarp();
+        b += 1; col += BUF_COLS; boff += 8u;
+        if (b == NBUF) { b = 0; col = 0; boff = 0; par ^= 1u; }
+        blo += 2u * (uint32_t)(B1_BYTES >> 4);
+        if (last) { u1 = 0; ++c1; blo = b1lo0; } else ++u1;
     }
 }
 
@@ -437,27 +539,180 @@ __device__ __forceinline__ void convert_unit(uint32_t addr)
 }
 
 // E12: set s (four warps) owns TMEM buffer s: for each of its units it converts D1 -> A2, then D2 -> A3
-__device__ __forceinline__ void convert_role(Smem& sm, uint32_t lane_addr, uint32_t set, uint32_t gt, uint32_t nunits, int lane)
+__device__ __noinline__ void convert_role(const Ctx& cx, uint32_t set)
 {
-    const uint32_t it0 = (set + NBUF - gt % NBUF) % NBUF;
-    uint32_t par = ((gt + it0) / NBUF) & 1u;
-    const uint32_t r1 = lane_addr + C_R1 + set * BUF_COLS, r2 = lane_addr + C_R2 + set * BUF_COLS;
-    uint64_t* const l1_done = &sm.l1_done[set];
-    uint64_t* const a2_ready = &sm.a2_ready[set];
-    uint64_t* const l2_done = &sm.l2_done[set];
-    uint64_t* const l3_ready = &sm.l3_ready[set];
+    const uint32_t it0 = (set + NBUF - cx.gt % NBUF) % NBUF;
+    uint32_t par = ((cx.gt + it0) / NBUF) & 1u;
+    const uint32_t r1 = cx.lane_addr + C_R1 + set * BUF_COLS, r2 = cx.lane_addr + C_R2 + set * BUF_COLS;
+    const uint32_t l1_done = BAR(l1_done, set), a2_ready = BAR(a2_ready, set), l2_done = BAR(l2_done, set), l3_ready = BAR(l3_ready, set);
+    const uint32_t nunits = cx.nunits;
+    const bool leader = cx.lane == 0;
 #pragma unroll 1
     for (uint32_t it = it0; it < nunits; it += NBUF, par ^= 1u) {
-        mbar_wait(l1_done, par);
+        mbar_wait_a_(cx, l1_done, par);
         tc_fence_after();
         convert_unit(r1);
         __syncwarp();
-        if (lane == 0) mbar_arrive(a2_ready);
-        mbar_wait(l2_done, par);
+        if (leader) mbar_arrive_a(a2_ready);
+        mbar_wait_a_(cx, l2_done, par);
         tc_fence_after();
         convert_unit(r2);
         __syncwarp();
-        if (lane == 0) mbar_arrive(l3_ready);
+        if (leader) mbar_arrive_a(l3_ready);
+    }
+}
+
+// E3: D3 -> offsets -> speculative env step of every (bar, inventory) row -> table.  Set s (four warps) owns TMEM
+// buffer s, i.e. the units with (global unit index % 3) == s: consecutive uses of its barriers, so every parity
+// wait is at most one phase away.  Outer loop over chunks (bar data, table buffer), inner loop over the set's
+// units of the chunk.
+template <bool FEE>
+__device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
+{
+    Smem& sm = *cx.sm;
+    const int lane = cx.lane;
+    const int row = cx.quarter * 32 + lane;
+    const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
+    const bool row_ok = row < TILE_BARS * 5;
+    const int64_t T = cx.T;
+    const uint32_t nchunks = cx.nchunks, UG = cx.UG, gc = cx.gc, gt = cx.gt;
+    const BarSig* sig = cx.sig; const BarPx* px = cx.px;
+    const double tick = cx.tick, phi = cx.phi, fee = cx.fee;
+    int2 kth = make_int2(0, 0), kth_n = make_int2(0, 0);
+    double2 ab = make_double2(0., 0.), ab_n = make_double2(0., 0.);
+    double mid = 0.0, mid_n = 0.0;
+    auto load_bar = [&](uint32_t c, int2& k, double2& q, double& m) {
+        const int64_t t = (int64_t)c * TILE_BARS + tl;
+        if (row_ok && t < T) {
+            k = __ldg(reinterpret_cast<const int2*>(&sig[t].ka1));
+            q = __ldg(reinterpret_cast<const double2*>(&px[t].ask));
+            m = __ldg(&px[t].mid_next);
+        }
+    };
+    const uint32_t taddr = cx.lane_addr + C_R3 + e3set * BUF_COLS;
+    const uint32_t l3_done = BAR(l3_done, e3set), l3_ready = BAR(l3_ready, e3set);
+    uint32_t par = ((gt + (e3set + NBUF - gt % NBUF) % NBUF) / NBUF) & 1u;       // parity of this set's first unit
+    uint32_t base3 = gt % NBUF;                                                 // (global index of the chunk's first unit) % 3
+    const uint32_t ug3 = UG % NBUF;
+    const int inv = iv - 2;
+    const bool leader = lane == 0;
+    if (nchunks > 0) load_bar(0, kth_n, ab_n, mid_n);
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        kth = kth_n; ab = ab_n; mid = mid_n;
+        if (c + 1 < nchunks) load_bar(c + 1, kth_n, ab_n, mid_n);               // prefetch the next chunk's bars
+        uint32_t up = e3set >= base3 ? e3set - base3 : e3set + NBUF - base3;    // first unit of the chunk that is ours
+        base3 += ug3; if (base3 >= NBUF) base3 -= NBUF;
+        if (up >= UG) continue;                                                 // (groups of 2 or 4: not every chunk has one)
+        const uint32_t q = gc + c, cbuf = q % 3u;
+        const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
+        mbar_wait_a_(cx, BAR(tab_empty, cbuf), ((q / 3u) & 1u) ^ 1u);                // walker has left this table buffer
+        const uint32_t tab_full = BAR(tab_full, cbuf);
+        double* tr = &sm.tab_r[cbuf][up * 2u][row];
+        uint8_t* tn = &sm.tab_n[cbuf][up * 2u][tl * 8 + iv];
+#pragma unroll 1
+        for (; up < UG; up += NBUF, par ^= 1u, tr += 2 * NBUF * TAB_R_STRIDE, tn += 2 * NBUF * TAB_N_STRIDE) {
+            mbar_wait_a_(cx, l3_done, par);
+            tc_fence_after();
+            uint32_t v[2][4];
+            tmem_ld4(taddr, v[0]);
+            tmem_ld4(taddr + S_D3, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (leader) mbar_arrive_a(l3_ready);                                 // accumulator drained
+            // Both tiles of the unit, branch-free so that the two dependency chains interleave.  Rows that
+            // are not valid compute on stale bar data and store nothing.
+            float ra[2], rb[2]; double rew[2]; uint32_t nxt[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                ra[j] = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));       // hi + lo halves of W3
+                rb[j] = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
+                const int ka = quantise(__fmul_rn(ra[j], 5.0f));                             // drl_engine.py:39
+                const int kb = quantise(__fmul_rn(rb[j], 5.0f));
+                // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
+                const bool fb = (inv < 2) && (kb < kth.y);                   // :34,:37
+                const bool fs = (inv > -2) && (ka < kth.x);                  // :35,:38
+                const double my_ask = add_rn(ab.x, mul_rn(int_to_double(ka), tick));
+                const double my_bid = sub_rn(ab.y, mul_rn(int_to_double(kb), tick));
+                double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
+                if (FEE) {
+                    leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));
+                    leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));
+                }
+                double pnl = 0.0;
+                pnl = fb ? add_rn(pnl, leg_b) : pnl;
+                pnl = fs ? add_rn(pnl, leg_s) : pnl;
+                const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
+                const double pen = mul_rn(phi, int_to_double(ninv < 0 ? -ninv : ninv));            // phi * |inv'|  (:57)
+                rew[j] = sub_rn(pnl, pen);                                                         // :58
+                nxt[j] = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    tr[j * TAB_R_STRIDE] = rew[j];
+                    tn[j * TAB_N_STRIDE] = (uint8_t)nxt[j];
+                }
+                if (cx.raw_table) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int64_t ind = cx.grp * cx.G + (int64_t)(up * 2u) + j;
+                        if (ind < cx.count) {
+                            float* o = cx.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
+                            __stcg(o, ra[j]); __stcg(o + 1, rb[j]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (leader) mbar_arrive_a(tab_full);
+        }
+    }
+}
+
+// walker: one lane per individual of the group
+__device__ __noinline__ void walker_role(const Ctx& cx)
+{
+    Smem& sm = *cx.sm;
+    const int g = cx.lane;
+    const int64_t ind = cx.grp * cx.G + g, T = cx.T;
+    const bool live = g < cx.G && ind < cx.count;
+    const uint32_t nchunks = cx.nchunks, gc = cx.gc;
+    int iv = 2, trades = 0;                                       // inventory 0
+    double total = 0.0;                                           // drl_engine.py:26
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t q = gc + c, cbuf = q % 3u, cpar = (q / 3u) & 1u;
+        mbar_wait_a_(cx, BAR(tab_full, cbuf), cpar);
+        if (live) {
+            const int64_t t0 = (int64_t)c * TILE_BARS;
+            const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
+            const uint8_t* nb = sm.tab_n[cbuf][g];
+            const double* rb = sm.tab_r[cbuf][g];
+            if (n == TILE_BARS && !cx.act_trace) walk_chunk<true>(nb, rb, n, iv, trades, total);      // every chunk but the last
+            else {
+                const int iv0 = iv;
+                walk_chunk<false>(nb, rb, n, iv, trades, total);
+                if (cx.act_trace) {                                    // audit: the offsets taken (second pass over the automaton)
+                    int w = iv0;
+                    for (int s = 0; s < n; ++s) {
+                        const float* o = cx.raw_table + (((int64_t)ind * T + t0 + s) * 5 + w) * 2;
+                        int32_t* at = cx.act_trace + ((int64_t)ind * T + t0 + s) * 2;
+                        at[0] = quantise(__fmul_rn(__ldcg(o), 5.0f));
+                        at[1] = quantise(__fmul_rn(__ldcg(o + 1), 5.0f));
+                        w = nb[s * 8 + w] & 7;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (cx.lane == 0) mbar_arrive_a(BAR(tab_empty, cbuf));
+    }
+    if (live) {
+        trades >>= 3;                                                  // walk_chunk counts in units of 8
+        if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
+        cx.fitness[ind] = total; cx.trades[ind] = trades;
     }
 }
 
@@ -495,7 +750,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may touch (warp % 4)
-    const uint32_t e3set = (uint32_t)(warp - WARP_E3) >> 2;     // E3 warps: set s owns TMEM buffer s, i.e. the units with (global index % 3) == s
+    const uint32_t e3set = (uint32_t)(warp - WARP_E3) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     if (warp < 4) {
         // the constant K-step shared by every layer-2 / layer-3 MMA: K slots 32, 33 = 1.0 (they meet the
@@ -511,8 +766,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     tc_fence_after();
 
     const PopArgs pop = resolve(a.mm);
-    uint32_t gt = 0;                               // units processed so far by this CTA (pipeline phase source)
-    uint32_t gc = 0;                               // chunks processed so far
+    Ctx cx;
+    cx.sm = &sm; cx.sm_addr = smem_u32(&sm); cx.tmem_base = tmem_base; cx.lane_addr = lane_addr;
+    cx.gt = 0; cx.gc = 0; cx.nchunks = nchunks; cx.UG = UG; cx.nunits = nunits;
+    cx.G = G; cx.lane = lane; cx.quarter = quarter; cx.T = T; cx.count = pop.count;
+    cx.sig = a.sig; cx.px = a.px; cx.a1 = a.a1; cx.tick = a.tick; cx.phi = a.phi; cx.fee = a.fee;
+    cx.fitness = a.fitness; cx.trades = a.trades; cx.raw_table = a.raw_table; cx.act_trace = a.act_trace;
 
     for (int64_t grp = blockIdx.x; grp * G < pop.count; grp += gridDim.x) {
         // ---------------- stage the group's weights (all warps) ----------------------------------
@@ -541,194 +800,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        if (warp < WARP_E3) {
-            convert_role(sm, lane_addr, (uint32_t)warp >> 2, gt, nunits, lane);
-        } else if (warp < WARP_L1) {
-            // =========================== E3 : offsets, speculative env step, table ================
-            const int row = quarter * 32 + lane;
-            const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
-            const bool row_ok = row < TILE_BARS * 5;
-            const uint32_t d_addr = lane_addr + C_R3;
-            int2 kth = make_int2(0, 0), kth_n = make_int2(0, 0);
-            double2 ab = make_double2(0., 0.), ab_n = make_double2(0., 0.);
-            double mid = 0.0, mid_n = 0.0;
-            auto load_bar = [&](uint32_t c, int2& k, double2& q, double& m) {
-                const int64_t t = (int64_t)c * TILE_BARS + tl;
-                if (row_ok && t < T) {
-                    k = __ldg(reinterpret_cast<const int2*>(&a.sig[t].ka1));
-                    q = __ldg(reinterpret_cast<const double2*>(&a.px[t].ask));
-                    m = __ldg(&a.px[t].mid_next);
-                }
-            };
-            // This set's units are those with (global unit index % 3) == e3set: always TMEM buffer e3set and
-            // consecutive uses of its barriers, so every parity wait is at most one phase away.
-            // Outer loop over chunks (bar data, table buffer), inner loop over the set's units of the chunk.
-            const uint32_t taddr = d_addr + e3set * BUF_COLS;
-            uint64_t* const l3_done = &sm.l3_done[e3set];
-            uint64_t* const l3_ready = &sm.l3_ready[e3set];
-            uint32_t par = ((gt + (e3set + NBUF - gt % NBUF) % NBUF) / NBUF) & 1u;       // parity of this set's first unit
-            uint32_t base3 = gt % NBUF;                                                 // (global index of the chunk's first unit) % 3
-            const uint32_t ug3 = UG % NBUF;
-            const int inv = iv - 2;
-            if (nchunks > 0) load_bar(0, kth_n, ab_n, mid_n);
-#pragma unroll 1
-            for (uint32_t c = 0; c < nchunks; ++c) {
-                kth = kth_n; ab = ab_n; mid = mid_n;
-                if (c + 1 < nchunks) load_bar(c + 1, kth_n, ab_n, mid_n);               // prefetch the next chunk's bars
-                uint32_t up = e3set >= base3 ? e3set - base3 : e3set + NBUF - base3;    // first unit of the chunk that is ours
-                base3 += ug3; if (base3 >= NBUF) base3 -= NBUF;
-                if (up >= UG) continue;                                                 // (groups of 2 or 4: not every chunk has one)
-                const uint32_t q = gc + c, cbuf = q % 3u;
-                const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
-                mbar_wait(&sm.tab_empty[cbuf], ((q / 3u) & 1u) ^ 1u);                   // walker has left this table buffer
-                double* tr = &sm.tab_r[cbuf][up * 2u][row];
-                uint8_t* tn = &sm.tab_n[cbuf][up * 2u][tl * 8 + iv];
-#pragma unroll 1
-                for (; up < UG; up += NBUF, par ^= 1u, tr += 2 * NBUF * TAB_R_STRIDE, tn += 2 * NBUF * TAB_N_STRIDE) {
-                    mbar_wait(l3_done, par);
-                    tc_fence_after();
-                    uint32_t v[2][4];
-                    tmem_ld4(taddr, v[0]);
-                    tmem_ld4(taddr + S_D3, v[1]);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(l3_ready);                                // accumulator drained
-                    // Both tiles of the unit, branch-free so that the two dependency chains interleave.  Rows that
-                    // are not valid compute on stale bar data and store nothing.
-                    float ra[2], rb[2]; double rew[2]; uint32_t nxt[2];
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        ra[j] = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));       // hi + lo halves of W3
-                        rb[j] = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
-                        const int ka = quantise(__fmul_rn(ra[j], 5.0f));                             // drl_engine.py:39
-                        const int kb = quantise(__fmul_rn(rb[j], 5.0f));
-                        // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                        const bool fb = (inv < 2) && (kb < kth.y);                   // :34,:37
-                        const bool fs = (inv > -2) && (ka < kth.x);                  // :35,:38
-                        const double my_ask = add_rn(ab.x, mul_rn(int_to_double(ka), a.tick));
-                        const double my_bid = sub_rn(ab.y, mul_rn(int_to_double(kb), a.tick));
-                        double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
-                        if (FEE) {
-                            leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
-                            leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
-                        }
-                        double pnl = 0.0;
-                        pnl = fb ? add_rn(pnl, leg_b) : pnl;
-                        pnl = fs ? add_rn(pnl, leg_s) : pnl;
-                        const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
-                        const double pen = mul_rn(a.phi, int_to_double(ninv < 0 ? -ninv : ninv));          // phi * |inv'|  (:57)
-                        rew[j] = sub_rn(pnl, pen);                                                         // :58
-                        nxt[j] = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            tr[j * TAB_R_STRIDE] = rew[j];
-                            tn[j * TAB_N_STRIDE] = (uint8_t)nxt[j];
-                        }
-                        if (a.raw_table) {
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const int64_t ind = grp * G + (int64_t)(up * 2u) + j;
-                                if (ind < pop.count) {
-                                    float* o = a.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
-                                    __stcg(o, ra[j]); __stcg(o + 1, rb[j]);
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.tab_full[cbuf]);
-                }
-            }
-        } else if (warp == WARP_L1) {
-            // =========================== L1 ISSUER + A1 TMA PRODUCER ===============================
-            // the whole warp runs the loop converged; one elected lane issues (same lane every time)
-            auto load_a1 = [&](uint32_t c) {
-                const uint32_t q = gc + c, slot = q % A1_STAGES, use = q / A1_STAGES;
-                mbar_wait(&sm.a1_empty[slot], (use & 1u) ^ 1u);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&sm.a1_full[slot], A1_BYTES);
-                    tma_bulk_g2s(sm.a1[slot], a.a1 + (size_t)c * A1_BYTES, A1_BYTES, &sm.a1_full[slot]);
-                }
-                __syncwarp();
-            };
-            for (uint32_t c = 0; c < nchunks && c < (uint32_t)(A1_STAGES - 1); ++c) load_a1(c);
-            // both tiles of a unit share the A1 tile and their B1 operands are adjacent in shared memory
-            // (4 row groups of 256 B each): ONE M=128, N=64, K=16 MMA fills D1 of both tiles
-            constexpr uint32_t ID64 = idesc(64);
-            const uint32_t b1lo0 = desc_lo(smem_u32(sm.b1[0]), 128), dhi = desc_hi(256);
-            uint32_t c1 = 0, u1 = 0, blo = b1lo0, alo = 0;
-            Slot sl; sl.init(gt);
-#pragma unroll 1
-            for (uint32_t it = 0; it < nunits; ++it) {
-                const uint32_t q = gc + c1, slot = q % A1_STAGES;
-                if (u1 == 0) {
-                    if (c1 + A1_STAGES - 1 < nchunks) load_a1(c1 + A1_STAGES - 1);
-                    mbar_wait(&sm.a1_full[slot], (q / A1_STAGES) & 1u);
-                    alo = desc_lo(smem_u32(sm.a1[slot]), 128);
-                }
-                mbar_wait(&sm.l2_done[sl.b], sl.par ^ 1u);            // layer 2 of the unit that used this buffer before has read its A operand
-                tc_fence_after();
-                const bool last = (u1 + 1 == UG);
-                if (elect_one()) {
-                    umma_ss2(tmem_base + C_R1 + sl.col, alo, dhi, blo, dhi, ID64, 0u);
-                    umma_commit(&sm.l1_done[sl.b]);
-                    if (last) umma_commit(&sm.a1_empty[slot]);
-                }
-                __syncwarp();
-                sl.advance<1>();
-                blo += 2u * (uint32_t)(B1_BYTES >> 4);
-                if (last) { u1 = 0; ++c1; blo = b1lo0; } else ++u1;
-            }
-        } else if (warp == WARP_L2) {
-            issue_role<2>(sm, tmem_base, gt, nunits, UG);
-        } else if (warp == WARP_L3) {
-            issue_role<3>(sm, tmem_base, gt, nunits, UG);
-        } else {
-            // =========================== WALKER : one lane per individual ==========================
-            const int g = lane;
-            const int64_t ind = grp * G + g;
-            const bool live = g < G && ind < pop.count;
-            int iv = 2, trades = 0;                                       // inventory 0
-            double total = 0.0;                                           // drl_engine.py:26
-#pragma unroll 1
-            for (uint32_t c = 0; c < nchunks; ++c) {
-                const uint32_t q = gc + c, cbuf = q % 3u, cpar = (q / 3u) & 1u;
-                mbar_wait(&sm.tab_full[cbuf], cpar);
-                if (live) {
-                    const int64_t t0 = (int64_t)c * TILE_BARS;
-                    const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
-                    const uint8_t* nb = sm.tab_n[cbuf][g];
-                    const double* rb = sm.tab_r[cbuf][g];
-                    if (n == TILE_BARS && !a.act_trace) walk_chunk<true>(nb, rb, n, iv, trades, total);      // every chunk but the last
-                    else {
-                        const int iv0 = iv;
-                        walk_chunk<false>(nb, rb, n, iv, trades, total);
-                        if (a.act_trace) {                                    // audit: the offsets taken (second pass over the automaton)
-                            int w = iv0;
-                            for (int s = 0; s < n; ++s) {
-                                const float* o = a.raw_table + (((int64_t)ind * T + t0 + s) * 5 + w) * 2;
-                                int32_t* at = a.act_trace + ((int64_t)ind * T + t0 + s) * 2;
-                                at[0] = quantise(__fmul_rn(__ldcg(o), 5.0f));
-                                at[1] = quantise(__fmul_rn(__ldcg(o + 1), 5.0f));
-                                w = nb[s * 8 + w] & 7;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tab_empty[cbuf]);
-            }
-            if (live) {
-                trades >>= 3;                                                  // walk_chunk counts in units of 8
-                if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
-                a.fitness[ind] = total; a.trades[ind] = trades;
-            }
-        }
-        gt += nunits;
-        gc += nchunks;
+        cx.grp = grp;
+        if (warp < WARP_E3) convert_role(cx, (uint32_t)warp >> 2);
+        else if (warp < WARP_L1) e3_role<FEE>(cx, e3set);
+        else if (warp == WARP_L1) l1_role(cx);
+        else if (warp == WARP_L2) issue_role<2>(cx);
+        else if (warp == WARP_L3) issue_role<3>(cx);
+        else walker_role(cx);
+
+        cx.gt += nunits;
+        cx.gc += nchunks;
         tc_fence_before();
         __syncthreads();                            // every role is done with this group's weights and tables
         tc_fence_after();
