@@ -14,6 +14,8 @@ step ends with the all-gather of the fitness / trade slices that a sharded GA ge
           genomes H2D + kernel + fitness/trades D2H inside the timed region
   roofline  FP32 CUDA-core roofline (compute-bound; 2368 algorithmic FLOP / env-step)
             against the FFMA peak measured live on this device; hbm sub-object for the bar/genome stream
+  tensor_core_h32   the same workload through the tensor-core rollout (sgmm_tc32.cu, SGMM_PRECISION_BF16):
+            device-timed value, e2e, tensor roofline (algorithmic and executed TFLOP/s), GA generations/s
   cpu_baseline / --impl reference   the CPU oracle port (oracle/sgmm_oracle.c, pthreads over all host
             cores) on a bounded sample of the same workload
 """
@@ -203,6 +205,21 @@ def run_ours(args):
                                                   trd_pin.data_ptr(), st))
         return float(fit_pin[0])
 
+    prm_tc = _lib.RolloutParams(PHI, FEE, 1, 0, 0, 0)             # SGMM_PRECISION_BF16: the tensor-core rollout (sgmm_tc32.cu)
+
+    def step_device_tc():
+        f, t = sgmm_b200.rollout_population(bun, g_dev, phi=PHI, fee_rate=FEE, precision="bf16")
+        if world > 1:
+            dist.all_gather_into_tensor(fit_all, f)
+            dist.all_gather_into_tensor(trd_all, t)
+        return f, t
+
+    def step_e2e_tc():
+        st = C.c_void_p(torch.cuda.current_stream(local).cuda_stream)
+        _lib.check(L.sgmm_rollout_population_host(bun.handle, C.byref(mm), None, C.byref(prm_tc), fit_pin.data_ptr(),
+                                                  trd_pin.data_ptr(), st))
+        return float(fit_pin[0])
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -212,6 +229,8 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step_device()
         step_e2e()
+        step_device_tc()
+        step_e2e_tc()
     barrier()
     fp32_peak = sgmm_b200.measure_fp32_peak(local)
 
@@ -239,22 +258,38 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop(t_wall0, t_wall1 + e2e_s)
+    # ---- the same two measurements for the tensor-core rollout (throughput mode, stated tolerance) ----
+    evs_tc = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    f_tc = None
+    for (e0, e1) in evs_tc:
+        flush.fill_(1)
+        e0.record()
+        f_tc, _ = step_device_tc()
+        e1.record()
+    barrier()
+    step_ms_tc = [e0.elapsed_time(e1) for (e0, e1) in evs_tc]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_tc()
+    barrier()
+    e2e_tc_s = time.perf_counter() - t0
+    clocks = sampler.stop(t_wall0, t_wall1 + e2e_s + e2e_tc_s + 1e-3 * sum(step_ms_tc))
 
-    tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    tt = torch.tensor([dev_ms, e2e_s, sum(step_ms_tc), e2e_tc_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = tt[0].item(), tt[1].item()
+    dev_ms, e2e_s, dev_ms_tc, e2e_tc_s = tt[0].item(), tt[1].item(), tt[2].item(), tt[3].item()
 
     # ---- GA generations/s (secondary metric; CUDA-graph replay of ask+rollout+tell+validate+select) ----
-    ga_rate, ga_small = None, None
+    ga_rate, ga_small, ga_rate_tc = None, None, None
     if rank == 0 and world == 1:
         from sgmm_b200 import synthetic
         from sgmm_b200.engine import DeviceGA
 
-        def ga_rate_of(train_b, val_b, pop, ngen):
+        def ga_rate_of(train_b, val_b, pop, ngen, precision=None):
             ga = DeviceGA(master, None, pop_size=pop, sigma=0.05, phi=PHI, fee_rate=FEE, use_arl=False, seed=0,
-                          max_generations=2 * ngen + 4, device=local)
+                          max_generations=2 * ngen + 4, device=local, precision=precision)
             ga.generation(train_b, val_b)
             torch.cuda.synchronize()
             graph = ga.capture(train_b, val_b)
@@ -270,6 +305,7 @@ def run_ours(args):
 
         val = sgmm_b200.Bundle.from_arrays(synthetic.synthetic_bundle(12, first_day=N_DAYS), stats, TICK, device=local)
         ga_rate = ga_rate_of(bun, val, P_PER_GPU, 5)
+        ga_rate_tc = ga_rate_of(bun, val, P_PER_GPU, 5, precision="bf16")
         # the reference's own scale (BASELINE configs[0]): population 50, one training day, one validation day
         d1 = synthetic.synthetic_bundle(1, first_day=200)
         st1 = synthetic.train_stats_of(d1)
@@ -317,6 +353,30 @@ def run_ours(args):
         G = HIDDEN * HIDDEN + 7 * HIDDEN + 2
         alg_bytes = P_PER_GPU * G * 4 + T * 48 + P_PER_GPU * 12       # genomes once + bars once + outputs
         cpu_rate, cores, n, Tc, dt, _ = cpu_port_rate(bundle, stats, genomes, target_seconds=12.0)
+        # tensor-core rollout: algorithmic FLOPs as above; EXECUTED tensor FLOPs per unit of two 128-row tiles
+        # (= 50 env-steps): L1 128x64x16, L2 2 x 128x32x48, L3 2 x 128x16x48, x2 FLOP per MAC
+        tc_value = steps_per_step * K / (dev_ms_tc * 1e-3)
+        tc_kernel_s = (dev_ms_tc / K) * 1e-3
+        tc_exec_flop_per_step = 2.0 * (128 * 64 * 16 + 2 * 128 * 32 * 48 + 2 * 128 * 16 * 48) / 50.0
+        tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        tc_alg_tflops = FLOP_PER_STEP * P_PER_GPU * T / tc_kernel_s / 1e12
+        tc = {"kernel": "tc32_kernel (sgmm_tc32.cu): all three policy layers on tcgen05 (bf16 x bf16 -> fp32 in TMEM, A operands "
+                        "chained through tensor memory), 5-inventory speculation, grouped GEMM over 14 individuals per CTA",
+              "precision": "SGMM_PRECISION_BF16: policy outputs within 0.12 tick of the fp32 oracle (tests/test_gpu_tc32.py), "
+                           "env step given the offsets bit-exact",
+              "value": tc_value, "unit": UNIT, "ms_per_step": dev_ms_tc / K, "per_step_ms": step_ms_tc,
+              "speedup_vs_exact_kernel": tc_value / value,
+              "e2e": {"value": steps_per_step * K / e2e_tc_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_tc_s / K,
+                      "h2d_bytes_per_step": P_PER_GPU * G * 4 * n_gpus, "d2h_bytes_per_step": P_PER_GPU * 12 * n_gpus},
+              "roofline": {"bound": "tensor", "achieved": tc_alg_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                           "frac": tc_alg_tflops / tensor_peak, "traffic": None,
+                           "executed_tflops": tc_exec_flop_per_step * P_PER_GPU * T / tc_kernel_s / 1e12,
+                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1400",
+                           "note": "algorithmic = 2368 FLOP/env-step; executed = 28836 FLOP/env-step (5-inventory speculation, "
+                                   "K padded to 16/48, N padded to 16 in layer 3); the kernel is bound by the CUDA-core side "
+                                   "(TMEM <-> register conversion, speculative fp64 env step), see profiles/"},
+              "ga_generations_per_sec": ga_rate_tc,
+              "checksum": float(f_tc.sum().item()) if f_tc is not None else None}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,7 +385,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": P_PER_GPU * G * 4 * n_gpus,
                     "d2h_bytes_per_step": P_PER_GPU * 12 * n_gpus, "ms_per_step": 1e3 * e2e_s / K,
                     "entry": "sgmm_rollout_population_host (pinned host genomes in, fitness/trades out; bundle resident)"},
-            "gpu_launches": K,
+            "gpu_launches": 2 * K,                      # K exact-kernel + K tensor-core rollouts in the device-timed regions
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak if fp32_peak else None,
@@ -356,6 +416,7 @@ def run_ours(args):
             "ga_generations_per_sec": ga_rate,
             "ga_generations_per_sec_config0_pop50_1day": ga_small,
             "h256_tensor_core": h256,
+            "tensor_core_h32": tc,
             "checksum": float(f_last.sum().item()) if f_last is not None else None,
         }
         print(json.dumps(out))

@@ -65,7 +65,7 @@ class GaConfig(C.Structure):
                 ("shard_first", C.c_int64), ("shard_count", C.c_int64),
                 ("sigma", C.c_float), ("patience", C.c_int32),
                 ("phi", C.c_double), ("fee_rate", C.c_double), ("seed", C.c_uint64),
-                ("max_generations", C.c_int32), ("reserved", C.c_int32)]
+                ("max_generations", C.c_int32), ("precision", C.c_int32)]
 
 
 class GaStatus(C.Structure):

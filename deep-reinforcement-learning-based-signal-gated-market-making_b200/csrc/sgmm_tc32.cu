@@ -523,17 +523,16 @@ __device__ __noinline__ void l1_role(const Ctx& cx)
 // of a unit, this warp's 32 rows
 __device__ __forceinline__ void convert_unit(uint32_t addr)
 {
-    uint32_t v[32], p[16];
-    tmem_ld32(addr, v);
+    uint32_t v0[32], v1[32];
+    tmem_ld32(addr, v0);
+    tmem_ld32(addr + S_D, v1);                                       // second tile of the unit
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-    tmem_ld32(addr + S_D, v);                                        // second tile of the unit
-    tmem_st16(addr, p);
-    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) v0[j] = pack_relu_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+    tmem_st16(addr, reinterpret_cast<uint32_t (&)[16]>(v0));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) p[j] = pack_relu_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-    tmem_st16(addr + S_D, p);
+    for (int j = 0; j < 16; ++j) v1[j] = pack_relu_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+    tmem_st16(addr + S_D, reinterpret_cast<uint32_t (&)[16]>(v1));
     tmem_st_wait();
     tc_fence_before();
 }

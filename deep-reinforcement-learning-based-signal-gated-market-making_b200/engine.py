@@ -262,11 +262,12 @@ class DeviceGA:
     the device, one call per generation, no host round trip."""
 
     def __init__(self, mm_master, adv_master=None, *, pop_size, sigma, phi, fee_rate, use_arl, seed,
-                 max_generations, patience=15, hidden=32, device=None, shard=None):
+                 max_generations, patience=15, hidden=32, device=None, shard=None, precision=None):
         self.device = torch.cuda.current_device() if device is None else int(device)
         first, count = (0, pop_size) if shard is None else shard
         cfg = _lib.GaConfig(hidden, int(bool(use_arl)), pop_size, first, count, float(sigma), patience,
-                            float(phi), float(fee_rate), int(seed), int(max_generations), 0)
+                            float(phi), float(fee_rate), int(seed), int(max_generations),
+                            _precision(precision, 32))
         m = np.ascontiguousarray(torch.as_tensor(mm_master).detach().cpu().numpy(), np.float32)
         a = None
         if use_arl:
@@ -340,10 +341,13 @@ class DeviceGA:
 class DRLEngine:
     """Drop-in for Env/drl_engine.py:69-178.  Same constructor, attributes and return values; the
     generation loop runs on the device (:class:`DeviceGA`).  Extra keyword arguments (``seed``,
-    ``device``, ``patience``) expose what the reference hard-codes or leaves to the global RNG."""
+    ``device``, ``patience``) expose what the reference hard-codes or leaves to the global RNG;
+    ``precision="bf16"`` evaluates the population with the tensor-core rollout (validation of the
+    best child stays on the exact fp32 kernel)."""
 
     def __init__(self, pop_size=50, sigma=0.05, phi=0.01, tick_size=0.01, fee_rate=0.0, use_arl=False,
-                 save_dir="checkpoints/drl", seed=0, device=None, patience=15):
+                 save_dir="checkpoints/drl", seed=0, device=None, patience=15, precision=None):
+        self.precision = precision      # None / "f32": bit-exact population evaluation; "bf16": tensor-core rollout
         self.phi = phi
         self.tick_size = tick_size
         self.fee_rate = fee_rate
@@ -368,7 +372,8 @@ class DRLEngine:
                       self.adv_evolver.master_policy.get_weights() if self.use_arl else None,
                       pop_size=self.mm_evolver.pop_size, sigma=self.mm_evolver.sigma, phi=self.phi,
                       fee_rate=self.fee_rate, use_arl=self.use_arl, seed=self.seed,
-                      max_generations=max(1, generations), patience=self.patience, device=dev)
+                      max_generations=max(1, generations), patience=self.patience, device=dev,
+                      precision=self.precision)
         try:
             logged = 0
             for gen in range(generations):

@@ -42,8 +42,14 @@ extern "C" {
 
 /* precision of the policy MLP */
 #define SGMM_PRECISION_F32   0      /* SGMM-F32 order on CUDA cores: bit-identical to the oracle (H=32) */
-#define SGMM_PRECISION_BF16  1      /* hidden layer on tcgen05 tensor cores, bf16 x bf16 -> fp32 in   */
-                                    /* TMEM, all 5 inventories of every bar evaluated at once (H=256) */
+#define SGMM_PRECISION_BF16  1      /* policy layers on tcgen05 tensor cores, bf16 x bf16 -> fp32 in  */
+                                    /* TMEM, all 5 inventories of every bar evaluated at once:        */
+                                    /*   H=32  all three layers as GEMMs chained through TMEM         */
+                                    /*         (sgmm_tc32.cu; params.units_per_lane = individuals per */
+                                    /*         CTA group, even, 0 = auto)                             */
+                                    /*   H=256 hidden layer (sgmm_spec256.cu)                         */
+                                    /* policy outputs within a stated tolerance of the fp32 oracle;   */
+                                    /* the env step given the offsets stays bit-exact                 */
 
 /* rollout flags */
 #define SGMM_FLAG_NONE       0
@@ -124,7 +130,7 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
                                  const sgmm_population* adv, const sgmm_rollout_params* params,
                                  double* fitness, int32_t* trades, void* stream);
 
-/* Audit variant of the tensor-core path (hidden = 256, SGMM_PRECISION_BF16): same kernel, plus
+/* Audit variant of the tensor-core paths (hidden = 32 or 256, SGMM_PRECISION_BF16): same kernel, plus
  *   raw_table  DEVICE float[count][T][5][2]  policy outputs for every (bar, inventory -2..2)
  *   act_trace  DEVICE int32[count][T][2]     the offsets actually taken along the walked trajectory
  * (either may be NULL).  Used to state the bf16 tolerance against the fp32 oracle and to replay the
@@ -203,7 +209,9 @@ typedef struct {
     double phi, fee_rate;
     uint64_t seed;
     int32_t max_generations;  /* history capacity                                                */
-    int32_t reserved;
+    int32_t precision;        /* SGMM_PRECISION_* of the POPULATION evaluation (0 = F32, bit-exact;  */
+                              /* BF16 = tensor-core rollout, use_arl must be 0).  The validation     */
+                              /* rollout of the best child always runs the exact F32 kernel.         */
 } sgmm_ga_config;
 
 typedef struct {

@@ -161,3 +161,36 @@ def test_golden_arl_checkpoint_audit_set(sg, orc):
     print(f"golden ARL audit set: max |d(raw*5)| = {worst:.4g} ticks, {flips} of 1920 recorded offsets flip "
           f"(all within {TAU_TICKS} tick of a rounding boundary of the fp32 result)")
     assert worst <= TAU_TICKS and flips_outside == 0
+
+
+def test_device_ga_with_tensor_core_population(sg, orc):
+    """sgmm_ga_config.precision = BF16: the population is evaluated by the tensor-core rollout, the
+    argmax / tell / master update are unchanged, and the validation rollout of the best child is the
+    exact fp32 kernel (bit-identical to the oracle)."""
+    from sgmm_b200 import synthetic, SgmmError
+    from sgmm_b200.engine import DeviceGA
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 95, 1, seed=4)
+    vb = synthetic.synthetic_bundle(1, first_day=96)
+    stats = synthetic.train_stats_of(synthetic.synthetic_bundle(1, first_day=95))
+    val = sg.Bundle.from_arrays(vb, stats, 0.001)
+    vz1, vz2 = orc.normalise(vb, stats)
+    ga = DeviceGA(master, None, pop_size=70, sigma=0.05, phi=1e-4, fee_rate=0.0, use_arl=False, seed=9,
+                  max_generations=4, precision="bf16")
+    try:
+        ga.generation(bun, val)
+        h = ga.history(1)
+        mm, adv, best = ga.masters()
+    finally:
+        ga.close()
+    f, t = sg.rollout_seeded(bun, torch.from_numpy(master).cuda(), count=70, sigma=0.05, seed=9, generation=0,
+                             phi=1e-4, precision="bf16")
+    f, t = f.cpu().numpy(), t.cpu().numpy()
+    i = int(np.argmax(f))
+    assert h["train_f"][0] == f[i] and h["train_trades"][0] == t[i]
+    child = orc.mutate(master, 0.05, 9, 0, i)
+    assert np.array_equal(mm, child)
+    fo, to = orc.rollout(child, None, (vz1, vz2) + vb[2:], 1e-4, 0.001, 0.0)
+    assert h["val_f"][0] == fo and h["val_trades"][0] == to
+    with pytest.raises(SgmmError):
+        DeviceGA(master, np.zeros(1250, np.float32), pop_size=8, sigma=0.05, phi=1e-4, fee_rate=0.0, use_arl=True,
+                 seed=1, max_generations=2, precision="bf16")
