@@ -84,3 +84,37 @@ class Bundle:
 
     def __len__(self):
         return self.T
+
+
+def bundle_windows(askprice1, bidprice1, p_buy_max, p_sell_min, event_step, n_signals, device=None):
+    """The per-day window loop of ``load_signals_bundle`` (pipeline/agent_trainer.py:47-73) on the device:
+    returns ``(mid_next, best_ask, best_bid, buy_max, sell_min)``, ``n_signals - 1`` float64 values each."""
+    if device is None:
+        device = torch.cuda.current_device()
+    cols = [np.ascontiguousarray(a, np.float64) for a in (askprice1, bidprice1, p_buy_max, p_sell_min)]
+    E = cols[0].size
+    if any(c.ndim != 1 or c.size != E for c in cols):
+        raise ValueError("event columns must be 1-D and of equal length")
+    m = max(int(n_signals) - 1, 0)
+    out = [np.empty(m, np.float64) for _ in range(5)]
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    _lib.check(_lib.lib().sgmm_bundle_windows_host(E, *[_ptr(c) for c in cols], int(event_step), int(n_signals),
+                                                   *[_ptr(o) for o in out], int(device), st))
+    return tuple(out)
+
+
+def day_bundle(event_df, s1_pred, s2_pred, event_step=19, device=None):
+    """One day of ``load_signals_bundle``: ``event_df`` is anything with the columns askprice1, bidprice1,
+    p_buy_max, p_sell_min (a DataFrame or a dict of arrays); returns that day's 7-tuple
+    ``(s1, s2, mid_next, best_ask, best_bid, buy_max, sell_min)`` (agent_trainer.py:47-73)."""
+    s1_pred, s2_pred = np.asarray(s1_pred), np.asarray(s2_pred).reshape(-1)
+    n = min(len(s1_pred), len(s2_pred))                                    # :47
+    col = (lambda k: np.asarray(event_df[k]))
+    mid, ask, bid, bmax, smin = bundle_windows(col("askprice1"), col("bidprice1"), col("p_buy_max"), col("p_sell_min"),
+                                               event_step, n, device)
+    return s1_pred[-n:][:-1] if n else s1_pred[:0], s2_pred[-n:][:-1] if n else s2_pred[:0], mid, ask, bid, bmax, smin
+
+
+def concat_days(days):
+    """``np.concatenate`` of per-day 7-tuples (agent_trainer.py:75-77): a multi-day bundle is ONE episode."""
+    return tuple(np.concatenate([d[k] for d in days]) for k in range(7))

@@ -278,6 +278,73 @@ int sgmm_rollout_table(const sgmm_bundle* bundle, const int32_t* table, const sg
                         trace, fitness, trades, (cudaStream_t)stream);
 }
 
+int sgmm_bundle_windows(int64_t n_events, const double* askprice1, const double* bidprice1, const double* p_buy_max,
+                        const double* p_sell_min, int64_t event_step, int64_t n_signals, double* mid_next, double* best_ask,
+                        double* best_bid, double* buy_max, double* sell_min, void* stream)
+{
+    if (n_events > 0 && n_signals > 1 && (!askprice1 || !bidprice1 || !p_buy_max || !p_sell_min || !mid_next || !best_ask || !best_bid || !buy_max || !sell_min)) {
+        set_error("NULL array"); return SGMM_ERR_INVALID;
+    }
+    return launch_bundle_windows(n_events, askprice1, bidprice1, p_buy_max, p_sell_min, event_step, n_signals,
+                                 mid_next, best_ask, best_bid, buy_max, sell_min, (cudaStream_t)stream);
+}
+
+int sgmm_bundle_windows_host(int64_t n_events, const double* askprice1, const double* bidprice1, const double* p_buy_max,
+                             const double* p_sell_min, int64_t event_step, int64_t n_signals, double* mid_next, double* best_ask,
+                             double* best_bid, double* buy_max, double* sell_min, int device, void* stream)
+{
+    if (n_events < 0 || n_signals < 0 || event_step <= 0) { set_error("negative size / non-positive step"); return SGMM_ERR_INVALID; }
+    if (n_signals <= 1 || n_events == 0) return SGMM_OK;
+    if ((n_events + event_step - 1) / event_step < n_signals) { set_error("more signals than sampled events"); return SGMM_ERR_INVALID; }
+    if (!askprice1 || !bidprice1 || !p_buy_max || !p_sell_min || !mid_next || !best_ask || !best_bid || !buy_max || !sell_min) { set_error("NULL array"); return SGMM_ERR_INVALID; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select CUDA device %d", device); return SGMM_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t e = (size_t)n_events, nb = (size_t)(n_signals - 1);
+    double* d = nullptr;
+    int rc = check_cuda(cudaMalloc(&d, (4 * e + 5 * nb) * sizeof(double)), "cudaMalloc(windows)");
+    const double* src[4] = {askprice1, bidprice1, p_buy_max, p_sell_min};
+    for (int k = 0; k < 4 && !rc; ++k) rc = check_cuda(cudaMemcpyAsync(d + k * e, src[k], e * sizeof(double), cudaMemcpyHostToDevice, st), "H2D events");
+    double* o = d + 4 * e;
+    if (!rc) rc = launch_bundle_windows(n_events, d, d + e, d + 2 * e, d + 3 * e, event_step, n_signals, o, o + nb, o + 2 * nb, o + 3 * nb, o + 4 * nb, st);
+    double* dst[5] = {mid_next, best_ask, best_bid, buy_max, sell_min};
+    for (int k = 0; k < 5 && !rc; ++k) rc = check_cuda(cudaMemcpyAsync(dst[k], o + k * nb, nb * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H bars");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "bundle_windows_host");
+    cudaFree(d);
+    return rc;
+}
+
+int sgmm_trace_analytics(int64_t n_traces, int64_t n_steps, const double* wealth, const double* cash, const double* mid,
+                         const int32_t* inventory, const uint8_t* is_trade, double* scratch, double* out, void* stream)
+{
+    return launch_analytics(n_traces, n_steps, wealth, cash, mid, inventory, is_trade, scratch, out, (cudaStream_t)stream);
+}
+
+int sgmm_trace_analytics_host(int64_t n_traces, int64_t n_steps, const double* wealth, const int32_t* inventory,
+                              const uint8_t* is_trade, double* out, int device, void* stream)
+{
+    if (n_traces < 0 || n_steps < 0) { set_error("negative size"); return SGMM_ERR_INVALID; }
+    if (n_traces == 0) return SGMM_OK;
+    if (!out || (n_steps > 0 && (!wealth || !inventory || !is_trade))) { set_error("NULL array"); return SGMM_ERR_INVALID; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select CUDA device %d", device); return SGMM_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)n_traces * (size_t)n_steps;
+    char* d = nullptr;
+    const size_t bytes = 2 * n * sizeof(double) + n * sizeof(int32_t) + ((n + 7) & ~(size_t)7) + (size_t)n_traces * 6 * sizeof(double) + 64;
+    int rc = check_cuda(cudaMalloc(&d, bytes), "cudaMalloc(analytics)");
+    double* dw = (double*)d; double* ds = dw + n; double* dout = ds + n;
+    int32_t* di = (int32_t*)(dout + (size_t)n_traces * 6); uint8_t* dt = (uint8_t*)(di + n);
+    if (!rc && n) rc = check_cuda(cudaMemcpyAsync(dw, wealth, n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D wealth");
+    if (!rc && n) rc = check_cuda(cudaMemcpyAsync(di, inventory, n * sizeof(int32_t), cudaMemcpyHostToDevice, st), "H2D inventory");
+    if (!rc && n) rc = check_cuda(cudaMemcpyAsync(dt, is_trade, n, cudaMemcpyHostToDevice, st), "H2D is_trade");
+    if (!rc) rc = launch_analytics(n_traces, n_steps, dw, nullptr, nullptr, di, dt, ds, dout, st);
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(out, dout, (size_t)n_traces * 6 * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H summary");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "trace_analytics_host");
+    cudaFree(d);
+    return rc;
+}
+
 int sgmm_env_init(sgmm_env_state* e, double phi, double tick_size, double fee_rate)
 {
     if (!e) { set_error("env is NULL"); return SGMM_ERR_INVALID; }

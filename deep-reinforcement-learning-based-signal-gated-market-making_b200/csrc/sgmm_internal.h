@@ -87,6 +87,12 @@ size_t tc32_a1_bytes(int64_t T);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,
                     const double* ask, const double* bid, cudaStream_t st);
 
+int launch_bundle_windows(int64_t E, const double* ask1, const double* bid1, const double* pmax, const double* pmin,
+                          int64_t step, int64_t n, double* mid_next, double* best_ask, double* best_bid,
+                          double* buy_max, double* sell_min, cudaStream_t st);
+int launch_analytics(int64_t B, int64_t T, const double* wealth, const double* cash, const double* mid,
+                     const int32_t* inventory, const uint8_t* is_trade, double* scratch, double* out, cudaStream_t st);
+
 inline int64_t genome_len(int H) { return (int64_t)H * H + 7 * (int64_t)H + 2; }
 
 }  // namespace sgmm

@@ -247,6 +247,42 @@ int sgmm_ga_history_host(sgmm_ga* ga, int32_t n, double* train_f, double* val_f,
                          int32_t* train_trades, int32_t* val_trades, float* sigma, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Upstream of the rollout: the per-day window loop of load_signals_bundle
+ * (pipeline/agent_trainer.py:47-73).  Inputs are one day's event frame columns (loader2.event_df:
+ * askprice1, bidprice1, p_buy_max, p_sell_min; n_events rows, NaN allowed in the last two) and
+ * n_signals = min(len(s1_pred), len(s2_pred)) (:47).  The events are sampled every event_step rows
+ * (:49), the last n_signals samples are kept, and for each consecutive pair the outputs are
+ *   buy_max / sell_min  NaN-skipping max / min over the INCLUSIVE window between the two samples (:54-59)
+ *   best_ask / best_bid of the current sample (:70-71),  mid_next = (ask + bid) / 2 of the next (:73)
+ * n_signals - 1 values each (none if n_signals <= 1).  SGMM_ERR_INVALID if n_signals exceeds the
+ * number of sampled events ceil(n_events / event_step).  z-normalisation and train_stats stay on the
+ * host with the caller's own numpy expression (they are float32 pairwise reductions of numpy).
+ * ------------------------------------------------------------------------------------------- */
+int sgmm_bundle_windows(int64_t n_events, const double* askprice1, const double* bidprice1,
+                        const double* p_buy_max, const double* p_sell_min, int64_t event_step, int64_t n_signals,
+                        double* mid_next, double* best_ask, double* best_bid, double* buy_max, double* sell_min,
+                        void* stream);                                   /* DEVICE pointers, no sync */
+int sgmm_bundle_windows_host(int64_t n_events, const double* askprice1, const double* bidprice1,
+                             const double* p_buy_max, const double* p_sell_min, int64_t event_step, int64_t n_signals,
+                             double* mid_next, double* best_ask, double* best_bid, double* buy_max, double* sell_min,
+                             int device, void* stream);                   /* HOST pointers, synchronises */
+
+/* ---------------------------------------------------------------------------------------------
+ * Downstream of the rollout: StrategyAnalytics.summary_dict (analytics/mm_analyzer.py:5-56) for a
+ * batch of n_traces traces of n_steps rows each (row-major [n_traces, n_steps]):
+ *   out[b] = { Total PnL, MAP (Risk), PnLMAP (Eff), Max DD, Sharpe, Trades }        float64[6]
+ * wealth may be NULL, in which case it is derived as cash + inventory * mid (Env/recorder.py:46) with
+ * mid[n_steps] shared by all traces (the sgmm_rollout_trace outputs plug in directly).
+ * scratch: DEVICE float64[n_traces, n_steps] workspace.  Reductions follow pandas / numpy's pairwise
+ * float64 summation order, so the Sharpe ratio is bit-identical to the reference's.
+ * ------------------------------------------------------------------------------------------- */
+int sgmm_trace_analytics(int64_t n_traces, int64_t n_steps, const double* wealth, const double* cash,
+                         const double* mid, const int32_t* inventory, const uint8_t* is_trade,
+                         double* scratch, double* out, void* stream);    /* DEVICE pointers, no sync */
+int sgmm_trace_analytics_host(int64_t n_traces, int64_t n_steps, const double* wealth, const int32_t* inventory,
+                              const uint8_t* is_trade, double* out, int device, void* stream);   /* HOST pointers */
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helper: sustained FP32 FFMA throughput of the device (TFLOP/s), the denominator of
  * the H=32 roofline (SURVEY.md section 8d asks for a measured FFMA peak).
  * ------------------------------------------------------------------------------------------- */

@@ -235,3 +235,35 @@ def rollout_population(bundle_z, phi, tick, fee, *, genomes=None, master=None, s
                                     _p(smin, _f64p), phi, tick, fee, _p(fit, _f64p), _p(trd, _i32p),
                                     nthreads)
     return fit, trd
+
+
+def bundle_windows(ask1, bid1, p_buy_max, p_sell_min, step, n):
+    """pipeline/agent_trainer.py:47-73 for one day: returns (mid_next, best_ask, best_bid, buy_max, sell_min)."""
+    a, b, mx, mn = (_f64(x) for x in (ask1, bid1, p_buy_max, p_sell_min))
+    m = max(int(n) - 1, 0)
+    out = [np.empty(m, np.float64) for _ in range(5)]
+    L = lib()
+    L.oracle_bundle_windows.restype = C.c_int64
+    r = L.oracle_bundle_windows(C.c_int64(len(a)), _p(a, _f64p), _p(b, _f64p), _p(mx, _f64p),
+                                _p(mn, _f64p), C.c_int64(int(step)), C.c_int64(int(n)),
+                                *[_p(o, _f64p) for o in out])
+    if r < 0:
+        raise ValueError("more signals than sampled events")
+    return tuple(o[:r] for o in out)
+
+
+ANALYTICS_KEYS = ("Total PnL", "MAP (Risk)", "PnLMAP (Eff)", "Max DD", "Sharpe", "Trades")
+
+
+def analytics(wealth, inventory, is_trade):
+    """analytics/mm_analyzer.py:5-56 summary of one trace -> float64[6] in ANALYTICS_KEYS order."""
+    w = _f64(wealth)
+    iv = np.ascontiguousarray(inventory, np.int32)
+    tr = np.ascontiguousarray(np.asarray(is_trade).astype(bool), np.uint8)
+    out = np.zeros(6, np.float64)
+    scratch = np.empty(max(len(w), 1), np.float64)
+    L = lib()
+    L.oracle_analytics.restype = None
+    L.oracle_analytics(C.c_int64(len(w)), _p(w, _f64p), _p(iv, _i32p), _p(tr, C.POINTER(C.c_uint8)),
+                       _p(scratch, _f64p), _p(out, _f64p))
+    return out
