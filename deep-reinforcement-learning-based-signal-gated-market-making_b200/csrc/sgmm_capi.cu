@@ -178,13 +178,13 @@ static int check_rollout_args(const sgmm_bundle* bundle, const sgmm_population* 
 {
     if (!bundle || !mm || !params) { set_error("NULL bundle / mm / params"); return SGMM_ERR_INVALID; }
     if (mm->count > 0 && (!fitness || !trades)) { set_error("NULL output array"); return SGMM_ERR_INVALID; }
-    if (params->precision != SGMM_PRECISION_F32 && params->precision != SGMM_PRECISION_BF16) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
+    if (params->precision != SGMM_PRECISION_F32 && params->precision != SGMM_PRECISION_BF16 && params->precision != SGMM_PRECISION_TF32) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
     if (mm->hidden == 256) {
-        if (params->precision != SGMM_PRECISION_BF16) { set_error("hidden=256 runs on the tensor cores: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 path is built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
+        if (params->precision != SGMM_PRECISION_BF16) { set_error("hidden=256 runs on the tensor cores in bf16: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 path and the tf32 path are built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
         if (adv) { set_error("the H=256 tensor-core rollout has no adversary path"); return SGMM_ERR_UNSUPPORTED; }
     } else if (mm->hidden == 32) {
-        if (params->precision == SGMM_PRECISION_BF16 && adv) { set_error("the H=32 tensor-core rollout (precision=SGMM_PRECISION_BF16) has no adversary path; use SGMM_PRECISION_F32"); return SGMM_ERR_UNSUPPORTED; }
-    } else if (params->precision != SGMM_PRECISION_F32) { set_error("precision=SGMM_PRECISION_BF16 needs hidden=32 or hidden=256"); return SGMM_ERR_UNSUPPORTED; }
+        if (params->precision != SGMM_PRECISION_F32 && adv) { set_error("the H=32 tensor-core rollout (precision BF16 / TF32) has no adversary path; use SGMM_PRECISION_F32"); return SGMM_ERR_UNSUPPORTED; }
+    } else if (params->precision != SGMM_PRECISION_F32) { set_error("the tensor-core precisions need hidden=32 (BF16 / TF32) or hidden=256 (BF16)"); return SGMM_ERR_UNSUPPORTED; }
     if (adv && adv->count != mm->count) { set_error("adv.count (%lld) != mm.count (%lld): MM i meets adversary i (Env/drl_engine.py:115)", (long long)adv->count, (long long)mm->count); return SGMM_ERR_INVALID; }
     if (adv && adv->hidden != 32) { set_error("adversary genomes are 1250-float TradingPolicy(32) genomes (models/model.py:63)"); return SGMM_ERR_INVALID; }
     return SGMM_OK;
@@ -200,8 +200,9 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
     DeviceGuard guard(bundle->device);
     if (mm->hidden == 256)
         return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
-    if (params->precision == SGMM_PRECISION_BF16)
-        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
+    if (params->precision != SGMM_PRECISION_F32)
+        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, nullptr, nullptr,
+                           (cudaStream_t)stream, params->precision == SGMM_PRECISION_TF32);
     return launch_rollout(bundle, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                           params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
 }
@@ -210,12 +211,13 @@ int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population*
                                double* fitness, int32_t* trades, float* raw_table, int32_t* act_trace, void* stream)
 {
     if (int rc = check_rollout_args(bundle, mm, nullptr, params, fitness, trades)) return rc;
-    if (params->precision != SGMM_PRECISION_BF16) { set_error("audit entry is for the tensor-core paths (precision=SGMM_PRECISION_BF16)"); return SGMM_ERR_INVALID; }
+    if (params->precision == SGMM_PRECISION_F32) { set_error("audit entry is for the tensor-core paths (precision BF16 / TF32)"); return SGMM_ERR_INVALID; }
     PopArgs pm;
     if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
     DeviceGuard guard(bundle->device);
     if (mm->hidden == 32)
-        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
+        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace,
+                           (cudaStream_t)stream, params->precision == SGMM_PRECISION_TF32);
     return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
 }
 
@@ -250,8 +252,9 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
     }
     if (mm->hidden == 256) {
         if (int rc = launch_spec256(b, pm, params->phi, params->fee_rate, d_fit, d_trd, nullptr, nullptr, st)) return rc;
-    } else if (params->precision == SGMM_PRECISION_BF16) {
-        if (int rc = launch_tc32(b, pm, params->phi, params->fee_rate, params->units_per_lane, d_fit, d_trd, nullptr, nullptr, st)) return rc;
+    } else if (params->precision != SGMM_PRECISION_F32) {
+        if (int rc = launch_tc32(b, pm, params->phi, params->fee_rate, params->units_per_lane, d_fit, d_trd, nullptr, nullptr, st,
+                                 params->precision == SGMM_PRECISION_TF32)) return rc;
     } else if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                                        params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
     if (int rc = check_cuda(cudaMemcpyAsync(fitness, d_fit, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H fitness")) return rc;

@@ -50,8 +50,9 @@ constexpr int GMAX = 16;                       // individuals per CTA group (eve
 constexpr int K1 = 16, K2 = 48;
 constexpr int A1_BYTES = TILE_ROWS * K1 * 2;   // 4096
 constexpr int B1_BYTES = H * K1 * 2;           // 1024
-constexpr int B2_BYTES = H * K2 * 2;           // 3072
-constexpr int B3_BYTES = 16 * K2 * 2;          // 1536
+constexpr int K2T = 40;                        // tf32 mode: 32 hidden + one K=8 bias step
+constexpr int B2_BYTES = H * K2T * 4;          // 5120  (bf16 mode uses the first H * K2 * 2 = 3072 bytes)
+constexpr int B3_BYTES = 16 * K2T * 4;         // 2560  (bf16 mode: 1536)
 constexpr int A1_STAGES = 4;
 constexpr int WARP_E3 = 12, WARP_L1 = 24, WARP_L2 = 25, WARP_L3 = 26;     // warp 27 = walker
 constexpr int NUM_THREADS = 896;
@@ -153,7 +154,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 // k-chunks 128 B apart, 8-row groups (K/8)*128 B apart
 __host__ __device__ __forceinline__ uint32_t canon(int r, int k, int K) { return (uint32_t)(((r >> 3) * (K >> 3) + (k >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2); }
 
+// the same for 32-bit (tf32) elements: a 16-byte core-matrix row holds 4 of them
+__host__ __device__ __forceinline__ uint32_t canon32(int r, int k, int K) { return (uint32_t)(((r >> 3) * (K >> 2) + (k >> 2)) * 128 + (r & 7) * 16 + (k & 3) * 4); }
+
 // instruction descriptor: c = f32 (bit 4), a = b = bf16 (bits 7, 10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+// tf32 operands: format code 2 at bits [7,10) and [10,13)
+__host__ __device__ constexpr uint32_t idesc_tf32(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24); }
 __host__ __device__ constexpr uint32_t idesc(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24); }
 
 __device__ __forceinline__ void umma_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc)
@@ -192,6 +198,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -205,6 +221,19 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi)
 {
     uint32_t r;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// fp32 -> tf32 (10-bit mantissa, round to nearest even), returned as fp32 bits with the low 13 bits clear
+__device__ __forceinline__ uint32_t tf32_bits(float x)
+{
+    uint32_t r;
+    asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t tf32_relu_bits(float x)
+{
+    uint32_t r;
+    asm("cvt.rn.relu.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -263,10 +292,13 @@ __global__ void tc32_a1_kernel(int64_t T, int64_t nchunks, const BarSig* __restr
     }
 }
 
-// one genome element -> its bf16 slots in the B operands of individual slot g
+// one genome element -> its slots in the B operands of individual slot g.  B1 (layer 1) is always the bf16
+// split; B2 / B3 are bf16 (K padded to 48) or tf32 (K padded to 40).
+template <bool TF32>
 __device__ __forceinline__ void scatter_weight(Smem& sm, int g, int e, float v)
 {
     auto put = [](uint8_t* base, uint32_t off, float x) { *reinterpret_cast<uint16_t*>(base + off) = bf16_bits(x); };
+    auto put32 = [](uint8_t* base, uint32_t off, uint32_t bits) { *reinterpret_cast<uint32_t*>(base + off) = bits; };
     if (e < 96) {                                      // W1[j, i]   (models/model.py:10)
         const int j = e / 3, i = e % 3;
         float h, m, l; split3(v, h, m, l);
@@ -282,6 +314,13 @@ __device__ __forceinline__ void scatter_weight(Smem& sm, int g, int e, float v)
         const int j = e - 96;
         const float h = bf16_round(v), m = bf16_round(__fadd_rn(v, -h));
         put(sm.b1[g], canon(j, 14, K1), h); put(sm.b1[g], canon(j, 15, K1), m);
+    } else if (TF32) {
+        // hi = tf32(v), lo = tf32(v - hi): biases and W3 carry both, W2 only hi
+        const uint32_t hb = tf32_bits(v), lb = tf32_bits(__fadd_rn(v, -__uint_as_float(hb)));
+        if (e < 1152) { put32(sm.b2[g], canon32((e - 128) >> 5, (e - 128) & 31, K2T), hb); }
+        else if (e < 1184) { put32(sm.b2[g], canon32(e - 1152, 32, K2T), hb); put32(sm.b2[g], canon32(e - 1152, 33, K2T), lb); }
+        else if (e < 1248) { const int o = (e - 1184) >> 5, k = (e - 1184) & 31; put32(sm.b3[g], canon32(o, k, K2T), hb); put32(sm.b3[g], canon32(o + 2, k, K2T), lb); }
+        else { const int o = e - 1248; put32(sm.b3[g], canon32(o, 32, K2T), hb); put32(sm.b3[g], canon32(o, 33, K2T), lb); }
     } else if (e < 1152) {                             // W2[j, k]
         const int j = (e - 128) >> 5, k = (e - 128) & 31;
         put(sm.b2[g], canon(j, k, K2), v);
@@ -372,6 +411,12 @@ __device__ __forceinline__ void umma_ts2(uint32_t d, uint32_t a_tmem, uint32_t b
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n}\n"
                  ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(id), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_ts2_tf32(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t id, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n}\n"
+                 ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(id), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_ss2(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t id, uint32_t acc)
 {
     asm volatile("{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %6, 0;\nmov.b64 ad, {%1, %2};\nmov.b64 bd, {%3, %4};\n"
@@ -435,18 +480,20 @@ __device__ __forceinline__ void umma_commit_a(uint32_t addr)
 }
 
 // L2 / L3 issuer: a converged warp; one elected lane issues the six MMAs of a unit and one commit
-template <int LAYER>
+template <int LAYER, bool TF32>
 __device__ __noinline__ void issue_role(const Ctx& cx)
 {
-    constexpr uint32_t ID = LAYER == 2 ? idesc(32) : idesc(16);
+    constexpr uint32_t ID = TF32 ? (LAYER == 2 ? idesc_tf32(32) : idesc_tf32(16)) : (LAYER == 2 ? idesc(32) : idesc(16));
     constexpr uint32_t DSTEP = LAYER == 2 ? S_D : S_D3;
     constexpr uint32_t BSTEP = (uint32_t)((LAYER == 2 ? B2_BYTES : B3_BYTES) >> 4);
+    constexpr uint32_t SBO = TF32 ? (K2T / 4) * 128 : (K2 / 8) * 128;           // distance between 8-row groups of the B tile
+    constexpr int KSTEPS = TF32 ? 4 : 2;                                         // data K-steps (K = 8 tf32 / 16 bf16 each)
     const uint32_t ready0 = LAYER == 2 ? BAR(a2_ready, 0) : BAR(l3_ready, 0);     // A operand written (L3: and previous D3 drained)
     const uint32_t done0 = LAYER == 2 ? BAR(l2_done, 0) : BAR(l3_done, 0);
     const uint32_t l3done0 = BAR(l3_done, 0);
     const uint32_t d0 = cx.tmem_base + (LAYER == 2 ? C_R2 : C_R3), a0 = cx.tmem_base + (LAYER == 2 ? C_R1 : C_R2);
     const uint32_t one = cx.tmem_base + C_ONE;
-    const uint32_t blo0 = desc_lo(cx.sm_addr + (uint32_t)(LAYER == 2 ? offsetof(Smem, b2) : offsetof(Smem, b3)), 128), bhi = desc_hi(768);
+    const uint32_t blo0 = desc_lo(cx.sm_addr + (uint32_t)(LAYER == 2 ? offsetof(Smem, b2) : offsetof(Smem, b3)), 128), bhi = desc_hi(SBO);
     const uint32_t UG = cx.UG, nunits = cx.nunits;
     uint32_t u = 0, blo = blo0;
     uint32_t b = cx.gt % NBUF, par = (cx.gt / NBUF) & 1u, col = b * BUF_COLS, boff = b * 8u;
@@ -457,12 +504,18 @@ __device__ __noinline__ void issue_role(const Ctx& cx)
         tc_fence_after();
         if (elect_one()) {
             const uint32_t d = d0 + col, aa = a0 + col;
-            umma_ts2(d, aa, blo, bhi, ID, 0u);
-            umma_ts2(d, aa + 8, blo + 16, bhi, ID, 1u);                       // +256 B per K=16 step
-            umma_ts2(d, one, blo + 32, bhi, ID, 1u);                          // bias step: A = the constant [1 1 0 ...] columns
-            umma_ts2(d + DSTEP, aa + S_D, blo + BSTEP, bhi, ID, 0u);          // second tile of the unit
-            umma_ts2(d + DSTEP, aa + S_D + 8, blo + BSTEP + 16, bhi, ID, 1u);
-            umma_ts2(d + DSTEP, one, blo + BSTEP + 32, bhi, ID, 1u);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {                                      // the two tiles of the unit
+                const uint32_t dj = d + (uint32_t)j * DSTEP, aj = aa + (uint32_t)j * S_D, bj = blo + (uint32_t)j * BSTEP;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {                             // +8 TMEM columns and +256 B of B per K-step
+                    if (TF32) umma_ts2_tf32(dj, aj + 8u * k, bj + 16u * k, bhi, ID, k > 0 ? 1u : 0u);
+                    else umma_ts2(dj, aj + 8u * k, bj + 16u * k, bhi, ID, k > 0 ? 1u : 0u);
+                }
+                // bias step: A = the constant [1 1 0 ...] columns
+                if (TF32) umma_ts2_tf32(dj, one, bj + 16u * KSTEPS, bhi, ID, 1u);
+                else umma_ts2(dj, one, bj + 16u * KSTEPS, bhi, ID, 1u);
+            }
             umma_commit_a(done0 + boff);
         }
         __syncwarp();
@@ -521,23 +574,34 @@ __device__ __noinline__ void l1_role(const Ctx& cx)
 
 // accumulator (fp32, TMEM) -> ReLU -> bf16 pairs written back IN PLACE as the next layer's A operand, both tiles
 // of a unit, this warp's 32 rows
+template <bool TF32>
 __device__ __forceinline__ void convert_unit(uint32_t addr)
 {
     uint32_t v0[32], v1[32];
     tmem_ld32(addr, v0);
     tmem_ld32(addr + S_D, v1);                                       // second tile of the unit
     tmem_ld_wait();
+    if (TF32) {                                                      // fp32 -> relu -> tf32, 32 columns back in place
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v0[j] = pack_relu_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
-    tmem_st16(addr, reinterpret_cast<uint32_t (&)[16]>(v0));
+        for (int j = 0; j < 32; ++j) v0[j] = tf32_relu_bits(__uint_as_float(v0[j]));
+        tmem_st32(addr, v0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v1[j] = pack_relu_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
-    tmem_st16(addr + S_D, reinterpret_cast<uint32_t (&)[16]>(v1));
+        for (int j = 0; j < 32; ++j) v1[j] = tf32_relu_bits(__uint_as_float(v1[j]));
+        tmem_st32(addr + S_D, v1);
+    } else {                                                         // fp32 -> relu -> bf16 pairs, 16 columns
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v0[j] = pack_relu_bf16(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+        tmem_st16(addr, reinterpret_cast<uint32_t (&)[16]>(v0));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v1[j] = pack_relu_bf16(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+        tmem_st16(addr + S_D, reinterpret_cast<uint32_t (&)[16]>(v1));
+    }
     tmem_st_wait();
     tc_fence_before();
 }
 
 // E12: set s (four warps) owns TMEM buffer s: for each of its units it converts D1 -> A2, then D2 -> A3
+template <bool TF32>
 __device__ __noinline__ void convert_role(const Ctx& cx, uint32_t set)
 {
     const uint32_t it0 = (set + NBUF - cx.gt % NBUF) % NBUF;
@@ -550,12 +614,12 @@ __device__ __noinline__ void convert_role(const Ctx& cx, uint32_t set)
     for (uint32_t it = it0; it < nunits; it += NBUF, par ^= 1u) {
         mbar_wait_a_(cx, l1_done, par);
         tc_fence_after();
-        convert_unit(r1);
+        convert_unit<TF32>(r1);
         __syncwarp();
         if (leader) mbar_arrive_a(a2_ready);
         mbar_wait_a_(cx, l2_done, par);
         tc_fence_after();
-        convert_unit(r2);
+        convert_unit<TF32>(r2);
         __syncwarp();
         if (leader) mbar_arrive_a(l3_ready);
     }
@@ -715,7 +779,7 @@ __device__ __noinline__ void walker_role(const Ctx& cx)
     }
 }
 
-template <bool FEE>
+template <bool FEE, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -754,7 +818,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     if (warp < 4) {
         // the constant K-step shared by every layer-2 / layer-3 MMA: K slots 32, 33 = 1.0 (they meet the
         // bias rows of B2 / B3), 34..47 = 0
-        uint32_t c[8] = {0x3F803F80u, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t c[8] = {TF32 ? 0x3F800000u : 0x3F803F80u, TF32 ? 0x3F800000u : 0u, 0, 0, 0, 0, 0, 0};
         tmem_st8(lane_addr + C_ONE, c);
         tmem_st_wait();
     }
@@ -785,7 +849,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 if (q < 312) src.at4(e0, v);
                 else { v[0] = src.at(e0); v[1] = src.at(e0 + 1); }
             }
-            if (e0 >= 128 && e0 < 1152) {                       // 4 consecutive k of one W2 row: one 8-byte store
+            if (!TF32 && e0 >= 128 && e0 < 1152) {              // 4 consecutive k of one W2 row: one 8-byte store
                 const int j = (e0 - 128) >> 5, k = (e0 - 128) & 31;
                 uint2 o;
                 o.x = bf16_bits(v[0]) | ((uint32_t)bf16_bits(v[1]) << 16);
@@ -793,18 +857,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 *reinterpret_cast<uint2*>(sm.b2[g] + canon(j, k, K2)) = o;
             } else {
                 const int n = q < 312 ? 4 : 2;
-                for (int i = 0; i < n; ++i) scatter_weight(sm, g, e0 + i, v[i]);
+                for (int i = 0; i < n; ++i) scatter_weight<TF32>(sm, g, e0 + i, v[i]);
             }
         }
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
         cx.grp = grp;
-        if (warp < WARP_E3) convert_role(cx, (uint32_t)warp >> 2);
+        if (warp < WARP_E3) convert_role<TF32>(cx, (uint32_t)warp >> 2);
         else if (warp < WARP_L1) e3_role<FEE>(cx, e3set);
         else if (warp == WARP_L1) l1_role(cx);
-        else if (warp == WARP_L2) issue_role<2>(cx);
-        else if (warp == WARP_L3) issue_role<3>(cx);
+        else if (warp == WARP_L2) issue_role<2, TF32>(cx);
+        else if (warp == WARP_L3) issue_role<3, TF32>(cx);
         else walker_role(cx);
 
         cx.gt += nunits;
@@ -848,7 +912,7 @@ int tc32_group_size(int64_t count, int sms)
 }
 
 int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
-                float* raw_table, int32_t* act_trace, cudaStream_t st)
+                float* raw_table, int32_t* act_trace, cudaStream_t st, bool tf32)
 {
     using namespace tc32;
     if (mm.count == 0) return SGMM_OK;
@@ -862,13 +926,15 @@ int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee,
     const int64_t groups = (mm.count + a.group - 1) / a.group;
     const int grid = (int)(groups < sms ? groups : sms);
     const size_t smem = sizeof(Smem) + 128;
-    static bool configured[2] = {false, false};
+    static bool configured[4] = {false, false, false, false};
     const bool has_fee = fee != 0.0;
-    auto kern = has_fee ? tc32_kernel<true> : tc32_kernel<false>;
-    if (!configured[has_fee]) {
+    const int variant = (has_fee ? 1 : 0) | (tf32 ? 2 : 0);
+    auto kern = tf32 ? (has_fee ? tc32_kernel<true, true> : tc32_kernel<false, true>)
+                     : (has_fee ? tc32_kernel<true, false> : tc32_kernel<false, false>);
+    if (!configured[variant]) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(tc32 smem)")) return rc;
-        configured[has_fee] = true;
+        configured[variant] = true;
     }
     kern<<<grid, NUM_THREADS, smem, st>>>(a);
     return check_cuda(cudaGetLastError(), "tc32_kernel launch");

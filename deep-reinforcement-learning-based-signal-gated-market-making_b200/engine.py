@@ -29,7 +29,7 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-PRECISION_F32, PRECISION_BF16 = 0, 1
+PRECISION_F32, PRECISION_BF16, PRECISION_TF32 = 0, 1, 2
 
 
 def _precision(precision, hidden):
@@ -41,6 +41,8 @@ def _precision(precision, hidden):
         return PRECISION_F32
     if precision in ("bf16", "tensor", PRECISION_BF16):
         return PRECISION_BF16
+    if precision in ("tf32", PRECISION_TF32):
+        return PRECISION_TF32
     raise ValueError(f"unknown precision {precision!r}")
 
 
@@ -129,7 +131,7 @@ def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, fi
     return fit, trd
 
 
-def rollout_tc_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0, hidden=32, group=0):
+def rollout_tc_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0, hidden=32, group=0, precision="bf16"):
     """Tensor-core rollout (hidden=32: sgmm_tc32.cu, hidden=256: sgmm_spec256.cu) with its audit
     outputs: returns ``(fitness, trades, raw_table float32[P,T,5,2], act_trace int32[P,T,2])`` as
     CUDA tensors -- the policy outputs for every (bar, inventory) and the offsets actually taken."""
@@ -140,7 +142,7 @@ def rollout_tc_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0, hidden=32, g
     raw = torch.zeros(P, T, 5, 2, dtype=torch.float32, device=g.device)
     act = torch.zeros(P, T, 2, dtype=torch.int32, device=g.device)
     mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
-    prm = _params(phi, fee_rate, units_per_lane=group, hidden=hidden, precision=PRECISION_BF16)
+    prm = _params(phi, fee_rate, units_per_lane=group, hidden=hidden, precision=precision)
     _lib.check(_lib.lib().sgmm_rollout_spec256_audit(bundle.handle, C.byref(mm), C.byref(prm), fit.data_ptr(),
                                                      trd.data_ptr(), raw.data_ptr(), act.data_ptr(),
                                                      _stream(bundle.device)))

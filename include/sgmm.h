@@ -51,6 +51,10 @@ extern "C" {
                                     /* policy outputs within a stated tolerance of the fp32 oracle;   */
                                     /* the env step given the offsets stays bit-exact                 */
 
+#define SGMM_PRECISION_TF32  2      /* H=32 only: as BF16 but layers 2 and 3 on tcgen05 kind::tf32 (fp32  */
+                                    /* activations in TMEM rounded to 10 mantissa bits, tf32 weights):    */
+                                    /* ~4x tighter policy outputs at ~equal speed                        */
+
 /* rollout flags */
 #define SGMM_FLAG_NONE       0
 

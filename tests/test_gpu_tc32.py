@@ -14,7 +14,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TAU_TICKS = 0.12         # stated bf16 tolerance on raw*5 (ticks) for offsets spanning +-10 ticks; measured max is printed
+# stated tolerance on raw*5 (ticks) for offsets spanning +-10 ticks, per precision; the measured maximum is printed
+TAU = {"bf16": 0.12, "tf32": 0.03}
+TAU_TICKS = TAU["bf16"]
 
 
 @pytest.fixture(scope="module")
@@ -42,7 +44,7 @@ def _setup(sg, orc, days, first_day, P, seed, T=None, out_scale=6.0):
     return bundle, (z1, z2) + bundle[2:], bun, master, genomes
 
 
-def _audit(orc, bz, genomes, raw, T):
+def _audit(orc, bz, genomes, raw, T, TAU_TICKS=TAU_TICKS):
     worst, flips_outside = 0.0, 0
     for i in range(genomes.shape[0]):
         for t in range(T):
@@ -56,20 +58,22 @@ def _audit(orc, bz, genomes, raw, T):
     return worst, flips_outside
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
 @pytest.mark.parametrize("fee", [0.0, 3e-4])
-def test_policy_outputs_within_tolerance_and_env_bit_exact(sg, orc, fee):
+def test_policy_outputs_within_tolerance_and_env_bit_exact(sg, orc, fee, precision):
+    TAU_TICKS = TAU[precision]
     bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 90, 5, seed=11)
     T = bun.T
-    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, fee_rate=fee, hidden=32)
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, fee_rate=fee, hidden=32, precision=precision)
     fit, trd, raw, act = fit.cpu().numpy(), trd.cpu().numpy(), raw.cpu().numpy(), act.cpu().numpy()
-    worst, flips_outside = _audit(orc, bz, genomes, raw, T)
+    worst, flips_outside = _audit(orc, bz, genomes, raw, T, TAU_TICKS)
     for i in range(genomes.shape[0]):
         fo, to, tro = orc.rollout(None, None, bz, 1e-4, 0.001, fee, forced_actions=act[i], trace=True)
         assert fo == fit[i] and to == trd[i], (i, fo, fit[i], to, trd[i])
         inv_before = np.concatenate([[0], tro["inventory"][:-1]])
         taken = np.rint(raw[i, np.arange(T), inv_before + 2] * np.float32(5.0)).astype(np.int32)
         assert np.array_equal(taken, act[i])
-    print(f"max |d(raw*5)| = {worst:.4g} ticks (tolerance {TAU_TICKS})")
+    print(f"{precision}: max |d(raw*5)| = {worst:.4g} ticks (tolerance {TAU_TICKS})")
     assert worst <= TAU_TICKS
     assert flips_outside == 0
 
@@ -77,9 +81,10 @@ def test_policy_outputs_within_tolerance_and_env_bit_exact(sg, orc, fee):
 @pytest.mark.parametrize("T,P,group", [(1, 3, 0), (24, 40, 0), (25, 150, 0), (26, 17, 16), (51, 33, 6), (130, 5, 2), (240, 300, 0)])
 def test_ragged_lengths_groups_and_many_individuals(sg, orc, T, P, group):
     """Tail chunks, partial groups (P not a multiple of the group), several groups per CTA."""
+    precision = "tf32" if (T % 2) else "bf16"
     bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 91, P, seed=T, T=T)
-    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, hidden=32, group=group)
-    f2, t2 = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, precision="bf16")
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, phi=1e-4, hidden=32, group=group, precision=precision)
+    f2, t2 = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, precision=precision)
     assert torch.equal(f2, fit) and torch.equal(t2, trd)
     fit, trd, act = fit.cpu().numpy(), trd.cpu().numpy(), act.cpu().numpy()
     for i in range(0, P, max(1, P // 9)):
@@ -128,7 +133,8 @@ def test_seeded_children_match_explicit_genomes(sg, orc):
     assert torch.equal(f_exp, f_seed) and torch.equal(t_exp, t_seed)
 
 
-def test_golden_arl_checkpoint_audit_set(sg, orc):
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_golden_arl_checkpoint_audit_set(sg, orc, precision):
     """The fixed audit set: the reference's shipped ARL agent on its own 960-bar test bundle (tests/golden,
     960/960 recorded actions).  On the (bar, inventory) pairs the recorded run visited, the tensor-core
     policy outputs are within tolerance of the fp32 oracle; a recorded offset may flip only where the
@@ -146,7 +152,8 @@ def test_golden_arl_checkpoint_audit_set(sg, orc):
     my_bid = b["arl.bid"] - b["arl.off_b"] * 0.001
     bun = sg.Bundle(z1, z2, b["arl.mid"], b["arl.ask"], b["arl.bid"],
                     np.where(fs == 1, my_ask, my_ask - 0.0005), np.where(fb == 1, my_bid, my_bid + 0.0005), 0.001)
-    fit, trd, raw, act = sg.rollout_tc_audit(bun, g.reshape(1, -1), phi=1e-4, hidden=32)
+    TAU_TICKS = TAU[precision]
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, g.reshape(1, -1), phi=1e-4, hidden=32, precision=precision)
     raw, act = raw.cpu().numpy()[0], act.cpu().numpy()[0]
     inv_prev = np.concatenate([[0], b["arl.inventory"][:-1]])
     worst, flips, flips_outside = 0.0, 0, 0
@@ -158,9 +165,16 @@ def test_golden_arl_checkpoint_audit_set(sg, orc):
         rec = np.array([b["arl.off_a"][t], b["arl.off_b"][t]])
         flips += int(np.sum(np.rint(q_k) != rec))
         flips_outside += int(np.sum((np.rint(q_k) != rec) & (margin > TAU_TICKS)))
-    print(f"golden ARL audit set: max |d(raw*5)| = {worst:.4g} ticks, {flips} of 1920 recorded offsets flip "
+    print(f"golden ARL audit set ({precision}): max |d(raw*5)| = {worst:.4g} ticks, {flips} of 1920 recorded offsets flip "
           f"(all within {TAU_TICKS} tick of a rounding boundary of the fp32 result)")
     assert worst <= TAU_TICKS and flips_outside == 0
+    if precision == "tf32":
+        # no recorded offset flips, so the tensor-core path walks the reference's shipped backtest EXACTLY:
+        # every action, the trade count, and the fitness (same fp64 sums in the same order) are the recorded ones
+        assert flips == 0
+        assert np.array_equal(act[:, 0], b["arl.off_a"]) and np.array_equal(act[:, 1], b["arl.off_b"])
+        assert int(trd.item()) == int(((fb == 1) | (fs == 1)).sum())
+        assert fit.item() == np.cumsum(b["arl.reward"])[-1]
 
 
 def test_device_ga_with_tensor_core_population(sg, orc):
