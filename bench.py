@@ -154,7 +154,7 @@ def run_reference(args):
                                       f"evaluate_individual, pthreads over {cores} host threads)"},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_ours(args):
@@ -435,13 +435,30 @@ def run_ours(args):
             "tensor_core_h32": tc,
             "checksum": float(f_last.sum().item()) if f_last is not None else None,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract goes to the real stdout; everything libraries print while the
+    benchmark runs (NCCL's version banner, for instance) was redirected to stderr."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line.encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the duration of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
