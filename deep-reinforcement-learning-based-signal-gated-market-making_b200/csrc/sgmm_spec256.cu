@@ -9,17 +9,24 @@
 // followed by a trivially cheap walk of the 5-state automaton.  5x the hidden-layer FLOPs, on a
 // pipe ~30x faster than the FP32 cores, and no step-to-step latency chain.
 //
-// One persistent CTA per SM, one individual at a time, warp-specialised:
-//   warps 0-3  epilogue : tcgen05.ld of the fp32 accumulator (lane = row), +b2, ReLU, layer 3
-//                         (256->2, thread-local), x5 + round-half-even, and the SPECULATIVE env step of
-//                         the row's (bar, inventory): fills, next inventory, fp64 reward
-//                         (Env/market_env.py:30-58) -> 32-byte table entry
-//   warps 4-7  producer : layer 1 (3->256) in fp32 SGMM order for the 5 inventories of 25 bars,
-//                         cvt.rn.relu.bf16x2, 128B-swizzled K-major A tile (4 k-blocks of 16 KB, ring)
-//   warp  8    MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                         (M=128, N=256, K=16) x16 per tile, bf16 x bf16 -> fp32 in TMEM
-//                         (2 x 256 columns, double-buffered); tcgen05.commit -> mbarriers
-//   warp  9    walker   : inv <- next[t][inv], total += reward[t][inv] (fp64, reference order),
+// One persistent CTA per SM, one individual at a time, warp-specialised.  Layers 2 AND 3 run on the tensor
+// cores; the CUDA cores only convert the accumulator in place (the structure of sgmm_tc32.cu):
+//   warps 0-3   epilogue: per tile, E3 of the previous tile then E2 of this one
+//                 E2      : tcgen05.ld of D2 (lane = row, 8 x 32 columns), +b2, cvt.rn.relu.bf16x2,
+//                           tcgen05.st of A3 IN PLACE (columns 0..127 of the same TMEM buffer)
+//                 E3      : tcgen05.ld of D3 (4 columns: W3 hi + lo), +b3, x5 + round-half-even, and the
+//                           SPECULATIVE env step of the row's (bar, inventory): fills, next inventory, fp64
+//                           reward (Env/market_env.py:30-58) -> 32-byte table entry
+//   warps 4-11  producer: layer 1 (3->256) in fp32 SGMM order for the 5 inventories of 25 bars,
+//                         cvt.rn.relu.bf16x2, 128B-swizzled K-major A tile (4 k-blocks of 16 KB, ring);
+//                         two warps per k-block, so the four k-blocks of a tile are produced in parallel
+//                         (a serial producer made the tile period 4 x its k-block latency: 3 900 of 5 400 cycles)
+//   warp  12    L2      : converged warp, one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                         (M=128, N=256, K=16) x16 per tile, A and B from shared memory, D2 in TMEM
+//                         (2 buffers x 256 columns)
+//   warp  13    L3      : (M=128, N=16, K=16) x16 per tile, A3 read FROM TENSOR MEMORY, B3 = W3 hi / lo rows
+//                         from shared memory, D3 into columns 128..143 of the same buffer (dead after E2)
+//   warp  14    walker  : inv <- next[t][inv], total += reward[t][inv] (fp64, reference order),
 //                         trades; fitness / trade count out (Env/drl_engine.py:54-67)
 // W2 (bf16, 128 KB, swizzled K-major B operand) stays resident in shared memory for the episode.
 //
@@ -42,9 +49,11 @@ constexpr int TILE_BARS = 25;                 // 25 bars x 5 inventories = 125 r
 constexpr int KBLK = 64;                      // bf16 elements per 128-byte swizzle row
 constexpr int NKB = H / KBLK;                 // 4 k-blocks
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;      // epilogue: 2 column halves x 4 TMEM lane quarters
-constexpr int WARP_MMA = 12, WARP_WALK = 13;
-constexpr int NUM_THREADS = 448;
+constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 8;      // epilogue warps 0-3 (one per TMEM lane quarter) run E3(i-1) then E2(i)
+constexpr int WARP_MMA = 12, WARP_L3 = 13, WARP_WALK = 14;
+constexpr int NUM_THREADS = 480;
+constexpr int B3_BYTES = 16 * H * 2;          // W3 hi (rows 0,1) and bf16 residual (rows 2,3), canonical K-major layout
+constexpr uint32_t C_D3 = 128;                // D3 lives in columns 128..143 of the buffer (free once E2 has read D2)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int64_t G = (int64_t)H * H + 7 * H + 2;       // 67330
 
@@ -59,11 +68,13 @@ struct __align__(32) TableEntry {
 struct Smem {
     uint8_t b_tile[NKB][H * 128];              // W2 bf16, [k-block][n][64] swizzled, 128 KB
     uint8_t a_tile[NKB][TILE_ROWS * 128];      // h1 bf16, [k-block][row][64] swizzled, 64 KB
-    float w1x[H], w1y[H], w1i[H], b1[H], b2[H], w3a[H], w3b[H];
+    uint8_t b3_tile[B3_BYTES];                 // layer-3 B operand (no swizzle: 8 x 16-byte core matrices)
+    float w1x[H], w1y[H], w1i[H], b1[H], b2[H];
     float b3[4];
     TableEntry table[2][TILE_ROWS];
-    float2 part[2][TILE_ROWS];                 // layer-3 partial sums of the upper column half
-    uint64_t a_full[NKB], a_empty[NKB], d_full[2], d_empty[2], t_full[2], t_empty[2];
+    // d_full: L2 committed (D2 complete); a3_ready: E2 wrote A3; l3_done: L3 committed (D3 complete);
+    // d_empty: E3 has read D3, the buffer may take the next D2
+    uint64_t a_full[NKB], a_empty[NKB], d_full[2], a3_ready[2], l3_done[2], d_empty[2], t_full[2], t_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -113,6 +124,45 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
 }
+// layer 3: A operand from tensor memory, B (no swizzle) from shared memory, N = 16
+constexpr uint32_t IDESC_L3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(IDESC_L3), "r"(accumulate) : "memory");
+}
+// K-major SWIZZLE_NONE descriptor (checked by tools/tc32_unit.cu): LBO = distance of the two 16-byte k-chunks of a
+// K=16 step, SBO = distance of 8-row groups
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t canon(int r, int k, int K) { return (uint32_t)(((r >> 3) * (K >> 3) + (k >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -167,9 +217,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
     const int64_t ntiles = (T + TILE_BARS - 1) / TILE_BARS;
 
     if (tid == 0) {
-        for (int i = 0; i < NKB; ++i) { mbar_init(&sm.a_full[i], NUM_PROD_WARPS); mbar_init(&sm.a_empty[i], 1); }
+        for (int i = 0; i < NKB; ++i) { mbar_init(&sm.a_full[i], NUM_PROD_WARPS / NKB); mbar_init(&sm.a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.d_full[i], 1); mbar_init(&sm.d_empty[i], NUM_EPI_WARPS);
+            mbar_init(&sm.d_full[i], 1); mbar_init(&sm.a3_ready[i], 4); mbar_init(&sm.l3_done[i], 1);
+            mbar_init(&sm.d_empty[i], 4);
             mbar_init(&sm.t_full[i], 4); mbar_init(&sm.t_empty[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,6 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = tid; i < B3_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(sm.b3_tile)[i] = make_uint4(0, 0, 0, 0);
     // rows 125..127 of the A tile are never produced: keep them finite
     for (int i = tid; i < NKB * TILE_ROWS * 128 / 16; i += NUM_THREADS)
         reinterpret_cast<uint4*>(&sm.a_tile[0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -212,8 +264,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 sm.w1x[j] = src.at(3 * j); sm.w1y[j] = src.at(3 * j + 1); sm.w1i[j] = src.at(3 * j + 2);
                 sm.b1[j] = src.at(3 * H + j);
                 sm.b2[j] = src.at(4 * H + (int64_t)H * H + j);
-                sm.w3a[j] = src.at(5 * H + (int64_t)H * H + j);
-                sm.w3b[j] = src.at(6 * H + (int64_t)H * H + j);
+            }
+            for (int q = tid; q < 2 * H; q += NUM_THREADS) {                  // W3[o, k]: row o = bf16(w), row o+2 = bf16 residual
+                const int o = q / H, k = q % H;
+                const float w = src.at(5 * H + (int64_t)H * H + q);
+                const float h = bf16_round(w), m = bf16_round(__fadd_rn(w, -h));
+                *reinterpret_cast<uint16_t*>(&sm.b3_tile[canon(o, k, H)]) = bf16_bits(h);
+                *reinterpret_cast<uint16_t*>(&sm.b3_tile[canon(o + 2, k, H)]) = bf16_bits(m);
             }
             if (tid < 2) sm.b3[tid] = src.at(7 * H + (int64_t)H * H + tid);
         }
@@ -221,70 +278,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
         __syncthreads();
 
         if (warp < NUM_EPI_WARPS) {
-            // =========================== EPILOGUE ==============================================
-            const int half = warp >> 2, quarter = warp & 3;      // column half, TMEM lane quarter (= warp % 4)
+            // =========================== EPILOGUE : E3 of tile it-1, then E2 of tile it =================
+            const int quarter = warp & 3;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
             const int row = quarter * 32 + lane;
             const int tl = row / 5, iv = row % 5;          // bar within the tile, inventory index (inv+2)
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-            const int col0 = half * (H / 2);
-            for (int64_t it = 0; it < ntiles; ++it) {
+            auto e2 = [&](int64_t it) {                    // D2 -> +b2 -> relu -> bf16 -> A3 in place
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
-                // bar data of this row's step: issued before the accumulator is even ready so that the
-                // L2 latency hides behind the MMA wait and the column loop
+                mbar_wait(&sm.d_full[buf], use & 1u);
+                tc_fence_after();
+                const uint32_t tbase = lane_addr + buf * 256u;
+                uint32_t v[2][32];
+                tmem_ld32(tbase, v[0]);
+#pragma unroll
+                for (int cc = 0; cc < H / 32; ++cc) {
+                    tmem_ld_wait();                                        // chunk cc has landed
+                    if (cc + 1 < H / 32) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
+                    const uint32_t* w = v[cc & 1];
+                    uint32_t p[16];
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cc * 32 + c]);
+                        const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(w[c]), __uint_as_float(w[c + 1])), make_float2(bb.x, bb.y));
+                        const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(w[c + 2]), __uint_as_float(w[c + 3])), make_float2(bb.z, bb.w));
+                        p[c >> 1] = pack_relu_bf16(x0.x, x0.y);
+                        p[(c >> 1) + 1] = pack_relu_bf16(x1.x, x1.y);
+                    }
+                    // columns 16cc..16cc+15 were read (as part of chunk cc/2) before they are overwritten: writes trail reads
+                    tmem_st16(tbase + (uint32_t)(cc * 16), p);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.a3_ready[buf]);
+            };
+            auto e3 = [&](int64_t it) {                    // D3 -> offsets -> speculative env step -> table
+                const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
+                // bar data of this row's step: issued before the accumulator is ready (L2 latency hides behind the wait)
                 const int64_t t = it * TILE_BARS + tl;
                 const bool valid = (row < TILE_BARS * 5) && (t < T);
                 const int64_t tc_ = valid ? t : 0;
                 int2 kth = make_int2(0, 0); double2 ab = make_double2(0., 0.); double mid = 0.0;
-                if (half == 0 && T > 0) {
+                if (T > 0) {
                     kth = __ldg(reinterpret_cast<const int2*>(&a.sig[tc_].ka1));
                     ab = __ldg(reinterpret_cast<const double2*>(&a.px[tc_].ask));
                     mid = __ldg(&a.px[tc_].mid_next);
                 }
-
-                mbar_wait(&sm.d_full[buf], use & 1u);
+                mbar_wait(&sm.l3_done[buf], use & 1u);
                 tc_fence_after();
-                float2 accA[4], accB[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { accA[q] = make_float2(0.f, 0.f); accB[q] = make_float2(0.f, 0.f); }
-                const uint32_t tbase = lane_addr + buf * 256u + (uint32_t)col0;
-                uint32_t v[2][32];
-                tmem_ld32(tbase, v[0]);
-#pragma unroll
-                for (int cc = 0; cc < H / 64; ++cc) {
-                    tmem_ld_wait();                                        // chunk cc has landed
-                    if (cc + 1 < H / 64) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
-                    const uint32_t* w = v[cc & 1];
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[col0 + cc * 32 + c]);
-                        const float4 wa = *reinterpret_cast<const float4*>(&sm.w3a[col0 + cc * 32 + c]);
-                        const float4 wb = *reinterpret_cast<const float4*>(&sm.w3b[col0 + cc * 32 + c]);
-                        float2 x0 = __fadd2_rn(make_float2(__uint_as_float(w[c]), __uint_as_float(w[c + 1])), make_float2(bb.x, bb.y));
-                        float2 x1 = __fadd2_rn(make_float2(__uint_as_float(w[c + 2]), __uint_as_float(w[c + 3])), make_float2(bb.z, bb.w));
-                        x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f);
-                        const int q = (c >> 2) & 1;
-                        accA[2 * q] = __ffma2_rn(x0, make_float2(wa.x, wa.y), accA[2 * q]);
-                        accB[2 * q] = __ffma2_rn(x0, make_float2(wb.x, wb.y), accB[2 * q]);
-                        accA[2 * q + 1] = __ffma2_rn(x1, make_float2(wa.z, wa.w), accA[2 * q + 1]);
-                        accB[2 * q + 1] = __ffma2_rn(x1, make_float2(wb.z, wb.w), accB[2 * q + 1]);
-                    }
-                }
-                accA[0] = __fadd2_rn(accA[0], accA[2]); accA[1] = __fadd2_rn(accA[1], accA[3]);
-                accB[0] = __fadd2_rn(accB[0], accB[2]); accB[1] = __fadd2_rn(accB[1], accB[3]);
-                // the accumulator has been read: hand the TMEM buffer back to the MMA warp
+                uint32_t v[4];
+                tmem_ld4(lane_addr + buf * 256u + C_D3, v);
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.d_empty[buf]);
-
-                // combine the two column halves: the upper half hands its partial sums over
-                float pa = __fadd_rn(__fadd_rn(accA[0].x, accA[1].x), __fadd_rn(accA[0].y, accA[1].y));
-                float pb = __fadd_rn(__fadd_rn(accB[0].x, accB[1].x), __fadd_rn(accB[0].y, accB[1].y));
-                if (half == 1) sm.part[g & 1u][row] = make_float2(pa, pb);
-                asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
-                if (half == 1) continue;
-                const float2 other = sm.part[g & 1u][row];
-                const float ra = __fadd_rn(__fadd_rn(pa, other.x), sm.b3[0]);
-                const float rb = __fadd_rn(__fadd_rn(pb, other.y), sm.b3[1]);
+                if (lane == 0) mbar_arrive(&sm.d_empty[buf]);                // the buffer may take the next D2
+                const float ra = __fadd_rn(__fadd_rn(__uint_as_float(v[0]), __uint_as_float(v[2])), sm.b3[0]);   // W3 hi + lo, + b3
+                const float rb = __fadd_rn(__fadd_rn(__uint_as_float(v[1]), __uint_as_float(v[3])), sm.b3[1]);
                 const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));          // drl_engine.py:39
                 const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
                 // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
@@ -319,90 +368,112 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 sm.table[buf][row] = e;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.t_full[buf]);
+            };
+            for (int64_t it = 0; it < ntiles; ++it) {
+                if (it > 0) e3(it - 1);
+                e2(it);
             }
+            if (ntiles > 0) e3(ntiles - 1);
         } else if (warp < NUM_EPI_WARPS + NUM_PROD_WARPS) {
             // =========================== PRODUCER ==============================================
-            const int ptid = tid - NUM_EPI_WARPS * 32;     // 0..127
-            const int c = ptid & 7;                        // this thread's 16-byte chunk (8 k) in every k-block
+            // Two warps per k-block: the four k-blocks of a tile are produced IN PARALLEL, each pair waiting only
+            // for its own slot (a ring of one tile: a serial producer made the tile period 4 x its k-block latency).
+            const int pw = warp - NUM_EPI_WARPS;           // 0..7
+            const int kb = pw >> 1;                        // this pair's k-block
+            const int gtid = (pw & 1) * 32 + lane;         // 0..63 within the pair
+            const int c = gtid & 7;                        // this thread's 16-byte chunk (8 k) of the k-block
+            const int k0 = kb * KBLK + c * 8;
+            // the thread's layer-1 weights are the same for every tile of the individual: registers
+            float2 wx[4], wy[4], wi[4], bb[4];
+            {
+                const float4 p0 = *reinterpret_cast<const float4*>(&sm.w1x[k0]), p1 = *reinterpret_cast<const float4*>(&sm.w1x[k0 + 4]);
+                wx[0] = make_float2(p0.x, p0.y); wx[1] = make_float2(p0.z, p0.w); wx[2] = make_float2(p1.x, p1.y); wx[3] = make_float2(p1.z, p1.w);
+                const float4 q0 = *reinterpret_cast<const float4*>(&sm.w1y[k0]), q1 = *reinterpret_cast<const float4*>(&sm.w1y[k0 + 4]);
+                wy[0] = make_float2(q0.x, q0.y); wy[1] = make_float2(q0.z, q0.w); wy[2] = make_float2(q1.x, q1.y); wy[3] = make_float2(q1.z, q1.w);
+                const float4 r0 = *reinterpret_cast<const float4*>(&sm.w1i[k0]), r1 = *reinterpret_cast<const float4*>(&sm.w1i[k0 + 4]);
+                wi[0] = make_float2(r0.x, r0.y); wi[1] = make_float2(r0.z, r0.w); wi[2] = make_float2(r1.x, r1.y); wi[3] = make_float2(r1.z, r1.w);
+                const float4 s0 = *reinterpret_cast<const float4*>(&sm.b1[k0]), s1 = *reinterpret_cast<const float4*>(&sm.b1[k0 + 4]);
+                bb[0] = make_float2(s0.x, s0.y); bb[1] = make_float2(s0.z, s0.w); bb[2] = make_float2(s1.x, s1.y); bb[3] = make_float2(s1.z, s1.w);
+            }
+            uint8_t* slab = &sm.a_tile[kb][0];
             for (int64_t it = 0; it < ntiles; ++it) {
                 const uint32_t g = gt + (uint32_t)it;
                 const int64_t t0 = it * TILE_BARS;
-                // the thread's (up to) two bars of this tile
-                float2 z[2]; bool ok[2]; int tl[2];
+                // the thread's (up to) four bars of this tile: tasks q = gtid + 64 m = (bar, chunk)
+                float2 z[4];
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const int q = ptid + 128 * m;          // task id: (bar, chunk)
-                    tl[m] = q >> 3;
-                    ok[m] = (tl[m] < TILE_BARS);
-                    const int64_t t = t0 + tl[m] < T ? t0 + tl[m] : T - 1;
-                    z[m] = ok[m] ? *reinterpret_cast<const float2*>(&a.sig[t].z1) : make_float2(0.f, 0.f);
+                for (int m = 0; m < 4; ++m) {
+                    const int tlm = (gtid >> 3) + 8 * m;
+                    const int64_t t = t0 + tlm < T ? t0 + tlm : T - 1;
+                    z[m] = (tlm < TILE_BARS) ? *reinterpret_cast<const float2*>(&a.sig[t].z1) : make_float2(0.f, 0.f);
                 }
-#pragma unroll 1
-                for (int kb = 0; kb < NKB; ++kb) {
-                    const int k0 = kb * KBLK + c * 8;
-                    float2 wx[4], wy[4], wi[4], bb[4];
-                    {
-                        const float4 p0 = *reinterpret_cast<const float4*>(&sm.w1x[k0]), p1 = *reinterpret_cast<const float4*>(&sm.w1x[k0 + 4]);
-                        wx[0] = make_float2(p0.x, p0.y); wx[1] = make_float2(p0.z, p0.w); wx[2] = make_float2(p1.x, p1.y); wx[3] = make_float2(p1.z, p1.w);
-                        const float4 q0 = *reinterpret_cast<const float4*>(&sm.w1y[k0]), q1 = *reinterpret_cast<const float4*>(&sm.w1y[k0 + 4]);
-                        wy[0] = make_float2(q0.x, q0.y); wy[1] = make_float2(q0.z, q0.w); wy[2] = make_float2(q1.x, q1.y); wy[3] = make_float2(q1.z, q1.w);
-                        const float4 r0 = *reinterpret_cast<const float4*>(&sm.w1i[k0]), r1 = *reinterpret_cast<const float4*>(&sm.w1i[k0 + 4]);
-                        wi[0] = make_float2(r0.x, r0.y); wi[1] = make_float2(r0.z, r0.w); wi[2] = make_float2(r1.x, r1.y); wi[3] = make_float2(r1.z, r1.w);
-                        const float4 s0 = *reinterpret_cast<const float4*>(&sm.b1[k0]), s1 = *reinterpret_cast<const float4*>(&sm.b1[k0 + 4]);
-                        bb[0] = make_float2(s0.x, s0.y); bb[1] = make_float2(s0.z, s0.w); bb[2] = make_float2(s1.x, s1.y); bb[3] = make_float2(s1.z, s1.w);
-                    }
-                    // slot kb of the ring: wait until the MMA of the previous tile has consumed it
-                    if (g > 0) mbar_wait(&sm.a_empty[kb], (g - 1) & 1u);
-                    uint8_t* slab = &sm.a_tile[kb][0];
+                // the slot: wait until the MMAs of the previous tile have consumed it
+                if (g > 0) mbar_wait(&sm.a_empty[kb], (g - 1) & 1u);
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        if (ok[m]) {
-                            float2 A[4];
+                for (int m = 0; m < 4; ++m) {
+                    const int tlm = (gtid >> 3) + 8 * m;
+                    if (tlm < TILE_BARS) {
+                        float2 A[4];
 #pragma unroll
-                            for (int p = 0; p < 4; ++p)          // SGMM-F32 layer 1: b1, +W1[.,0] z1, +W1[.,1] z2
-                                A[p] = __ffma2_rn(wy[p], make_float2(z[m].y, z[m].y), __ffma2_rn(wx[p], make_float2(z[m].x, z[m].x), bb[p]));
+                        for (int p = 0; p < 4; ++p)          // SGMM-F32 layer 1: b1, +W1[.,0] z1, +W1[.,1] z2
+                            A[p] = __ffma2_rn(wy[p], make_float2(z[m].y, z[m].y), __ffma2_rn(wx[p], make_float2(z[m].x, z[m].x), bb[p]));
 #pragma unroll
-                            for (int iv = 0; iv < 5; ++iv) {
-                                const float inv2 = (float)(iv - 2) * 0.5f;       // drl_engine.py:35
-                                uint4 o;
-                                float2 v0 = __ffma2_rn(wi[0], make_float2(inv2, inv2), A[0]);
-                                float2 v1 = __ffma2_rn(wi[1], make_float2(inv2, inv2), A[1]);
-                                float2 v2 = __ffma2_rn(wi[2], make_float2(inv2, inv2), A[2]);
-                                float2 v3 = __ffma2_rn(wi[3], make_float2(inv2, inv2), A[3]);
-                                o.x = pack_relu_bf16(v0.x, v0.y); o.y = pack_relu_bf16(v1.x, v1.y);
-                                o.z = pack_relu_bf16(v2.x, v2.y); o.w = pack_relu_bf16(v3.x, v3.y);
-                                const int r = tl[m] * 5 + iv;
-                                *reinterpret_cast<uint4*>(slab + swz(r, c)) = o;
-                            }
+                        for (int iv = 0; iv < 5; ++iv) {
+                            const float inv2 = (float)(iv - 2) * 0.5f;       // drl_engine.py:35
+                            uint4 o;
+                            float2 v0 = __ffma2_rn(wi[0], make_float2(inv2, inv2), A[0]);
+                            float2 v1 = __ffma2_rn(wi[1], make_float2(inv2, inv2), A[1]);
+                            float2 v2 = __ffma2_rn(wi[2], make_float2(inv2, inv2), A[2]);
+                            float2 v3 = __ffma2_rn(wi[3], make_float2(inv2, inv2), A[3]);
+                            o.x = pack_relu_bf16(v0.x, v0.y); o.y = pack_relu_bf16(v1.x, v1.y);
+                            o.z = pack_relu_bf16(v2.x, v2.y); o.w = pack_relu_bf16(v3.x, v3.y);
+                            const int r = tlm * 5 + iv;
+                            *reinterpret_cast<uint4*>(slab + swz(r, c)) = o;
                         }
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.a_full[kb]);
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.a_full[kb]);
             }
         } else if (warp == WARP_MMA) {
-            // =========================== MMA ISSUER ============================================
-            if (lane == 0) {
-                for (int64_t it = 0; it < ntiles; ++it) {
-                    const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
-                    mbar_wait(&sm.d_empty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator
+            // =========================== L2 ISSUER (converged warp, one elected lane issues) ===========
+            for (int64_t it = 0; it < ntiles; ++it) {
+                const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
+                mbar_wait(&sm.d_empty[buf], (use & 1u) ^ 1u);              // E3 has read the D3 that lived in this buffer
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * 256u;
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&sm.a_full[kb], g & 1u);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + buf * 256u;
-                    for (int kb = 0; kb < NKB; ++kb) {
-                        mbar_wait(&sm.a_full[kb], g & 1u);
-                        tc_fence_after();
+                    if (elect_one()) {
                         const uint64_t ad = make_desc(smem_u32(&sm.a_tile[kb][0]));
                         const uint64_t bd = make_desc(smem_u32(&sm.b_tile[kb][0]));
 #pragma unroll
                         for (int k = 0; k < KBLK / UMMA_K; ++k)              // +32 B per K=16 step inside the swizzle atom
                             umma(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
                         umma_commit(&sm.a_empty[kb]);                        // slot free once these MMAs retire
+                        if (kb == NKB - 1) umma_commit(&sm.d_full[buf]);     // accumulator complete
                     }
-                    umma_commit(&sm.d_full[buf]);                            // accumulator complete
+                    __syncwarp();
                 }
             }
-            __syncwarp();
+        } else if (warp == WARP_L3) {
+            // =========================== L3 ISSUER: D3[128,16] = A3 (TMEM) x B3^T ====================
+            const uint64_t bd0 = make_desc_ns(smem_u32(sm.b3_tile), 128, (H / 8) * 128);
+            for (int64_t it = 0; it < ntiles; ++it) {
+                const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
+                mbar_wait(&sm.a3_ready[buf], use & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t base = tmem_base + buf * 256u;
+#pragma unroll
+                    for (int k = 0; k < H / UMMA_K; ++k)                     // 8 TMEM columns and 256 B of B3 per K=16 step
+                        umma_ts(base + C_D3, base + (uint32_t)(k * 8), bd0 + (uint64_t)(k * 16), k != 0 ? 1u : 0u);
+                    umma_commit(&sm.l3_done[buf]);
+                }
+                __syncwarp();
+            }
         } else {
             // =========================== WALKER ================================================
             if (lane == 0) {
