@@ -32,9 +32,14 @@ for P in (50, 2048, 4096, 8192, 16384):
         "explicit+adversary": lambda: sgmm_b200.rollout_population(bun, g, adv, phi=1e-4),
         "seeded": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4),
         "seeded+adversary": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, adv_master=advm, phi=1e-4),
+        "tensor tf32 explicit": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, precision="tf32"),
+        "tensor tf32 explicit+fee": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, fee_rate=3e-4, precision="tf32"),
+        "tensor tf32 seeded": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4, precision="tf32"),
+        "tensor bf16 explicit": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, precision="bf16"),
+        "tensor bf16 seeded": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4, precision="bf16"),
     }
     for name, fn in cases.items():
         ms = timed(fn)
         rows.append({"P": P, "T": T, "case": name, "ms": round(ms, 3), "G_env_steps_per_s": round(P * T / ms / 1e6, 3)})
         print(rows[-1], flush=True)
-json.dump(rows, open("gpurun_out/config_matrix_r1.json", "w"), indent=1)
+json.dump(rows, open("gpurun_out/config_matrix_r1b.json", "w"), indent=1)
