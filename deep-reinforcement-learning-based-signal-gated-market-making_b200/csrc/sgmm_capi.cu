@@ -178,7 +178,7 @@ static int check_rollout_args(const sgmm_bundle* bundle, const sgmm_population* 
 {
     if (!bundle || !mm || !params) { set_error("NULL bundle / mm / params"); return SGMM_ERR_INVALID; }
     if (mm->count > 0 && (!fitness || !trades)) { set_error("NULL output array"); return SGMM_ERR_INVALID; }
-    if (params->precision != SGMM_PRECISION_F32 && params->precision != SGMM_PRECISION_BF16 && params->precision != SGMM_PRECISION_TF32) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
+    if (params->precision != SGMM_PRECISION_F32 && params->precision != SGMM_PRECISION_BF16 && params->precision != SGMM_PRECISION_TF32 && params->precision != SGMM_PRECISION_F16) { set_error("unknown precision %d", params->precision); return SGMM_ERR_INVALID; }
     if (mm->hidden == 256) {
         if (params->precision != SGMM_PRECISION_BF16) { set_error("hidden=256 runs on the tensor cores in bf16: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 path and the tf32 path are built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
         if (adv) { set_error("the H=256 tensor-core rollout has no adversary path"); return SGMM_ERR_UNSUPPORTED; }
@@ -202,7 +202,7 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
         return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
     if (params->precision != SGMM_PRECISION_F32)
         return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, nullptr, nullptr,
-                           (cudaStream_t)stream, params->precision == SGMM_PRECISION_TF32);
+                           (cudaStream_t)stream, tc32_mode_of(params->precision));
     return launch_rollout(bundle, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                           params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
 }
@@ -217,7 +217,7 @@ int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population*
     DeviceGuard guard(bundle->device);
     if (mm->hidden == 32)
         return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace,
-                           (cudaStream_t)stream, params->precision == SGMM_PRECISION_TF32);
+                           (cudaStream_t)stream, tc32_mode_of(params->precision));
     return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
 }
 
@@ -254,7 +254,7 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
         if (int rc = launch_spec256(b, pm, params->phi, params->fee_rate, d_fit, d_trd, nullptr, nullptr, st)) return rc;
     } else if (params->precision != SGMM_PRECISION_F32) {
         if (int rc = launch_tc32(b, pm, params->phi, params->fee_rate, params->units_per_lane, d_fit, d_trd, nullptr, nullptr, st,
-                                 params->precision == SGMM_PRECISION_TF32)) return rc;
+                                 tc32_mode_of(params->precision))) return rc;
     } else if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                                        params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
     if (int rc = check_cuda(cudaMemcpyAsync(fitness, d_fit, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H fitness")) return rc;

@@ -153,7 +153,7 @@ int sgmm_ga_create(sgmm_ga** out, const sgmm_ga_config* cfg, const float* mm_mas
     if (!out || !cfg || !mm_master) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
     *out = nullptr;
     if (cfg->hidden != 32) { set_error("hidden=%d: GA rollouts are built for H=32", cfg->hidden); return SGMM_ERR_UNSUPPORTED; }
-    if (cfg->precision != SGMM_PRECISION_F32 && cfg->precision != SGMM_PRECISION_BF16 && cfg->precision != SGMM_PRECISION_TF32) { set_error("unknown precision %d", cfg->precision); return SGMM_ERR_INVALID; }
+    if (cfg->precision != SGMM_PRECISION_F32 && cfg->precision != SGMM_PRECISION_BF16 && cfg->precision != SGMM_PRECISION_TF32 && cfg->precision != SGMM_PRECISION_F16) { set_error("unknown precision %d", cfg->precision); return SGMM_ERR_INVALID; }
     if (cfg->precision != SGMM_PRECISION_F32 && cfg->use_arl) { set_error("the tensor-core population evaluation has no adversary path: use precision F32 with use_arl"); return SGMM_ERR_UNSUPPORTED; }
     if (cfg->pop_size <= 0 || cfg->shard_first < 0 || cfg->shard_count < 0 ||
         cfg->shard_first + cfg->shard_count > cfg->pop_size) { set_error("bad population / shard bounds"); return SGMM_ERR_INVALID; }
@@ -233,7 +233,7 @@ int sgmm_ga_evaluate(sgmm_ga* ga, const sgmm_bundle* train, void* stream)
     adv.master = ga->adv_master; adv.sigma_dev = &ga->st->adv_sigma; adv.seed = c.seed ^ ADV_SEED_FLIP;
     if (c.precision != SGMM_PRECISION_F32)                      // tensor-core population evaluation (no adversary path)
         return launch_tc32(train, mm, c.phi, c.fee_rate, 0, ga->fit_all + c.shard_first, ga->trd_all + c.shard_first,
-                           nullptr, nullptr, (cudaStream_t)stream, c.precision == SGMM_PRECISION_TF32);
+                           nullptr, nullptr, (cudaStream_t)stream, tc32_mode_of(c.precision));
     return launch_rollout(train, mm, c.use_arl ? &adv : nullptr, c.hidden, c.phi, c.fee_rate, 0, 0,
                           ga->fit_all + c.shard_first, ga->trd_all + c.shard_first, (cudaStream_t)stream);
 }

@@ -81,7 +81,8 @@ int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const
 int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades,
                    float* raw_table, int32_t* act_trace, cudaStream_t st);
 int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
-                float* raw_table, int32_t* act_trace, cudaStream_t st, bool tf32 = false);
+                float* raw_table, int32_t* act_trace, cudaStream_t st, int mode = 0);   // mode: 0 bf16, 1 tf32, 2 f16
+inline int tc32_mode_of(int precision) { return precision == SGMM_PRECISION_TF32 ? 1 : (precision == SGMM_PRECISION_F16 ? 2 : 0); }
 int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st);
 size_t tc32_a1_bytes(int64_t T);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,

@@ -34,6 +34,7 @@
 // tests/test_gpu_tc32.py states the tolerance against the fp32 oracle and checks that GIVEN the offsets
 // the kernel took, fills / inventory / trades / rewards / fitness are bit-identical to the oracle.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
@@ -68,6 +69,8 @@ constexpr uint32_t NBUF = 3, BUF_COLS = 160;
 constexpr uint32_t C_R1 = 0, C_R2 = 64, C_R3 = 128, C_ONE = 480;
 constexpr uint32_t S_D = 32, S_D3 = 16;
 constexpr int64_t G32 = 1250;
+// operand precision of layers 2 and 3 (layer 1 is always the bf16 split): template parameter of the kernel
+constexpr int M_BF16 = 0, M_TF32 = 1, M_F16 = 2;
 constexpr int TAB_R_STRIDE = TILE_ROWS + 1;    // doubles per individual: 258 words -> walker lanes hit distinct banks
 constexpr int TAB_N_STRIDE = TILE_BARS * 8;    // bytes per individual: 50 words -> distinct bank pairs
 
@@ -158,6 +161,11 @@ __host__ __device__ __forceinline__ uint32_t canon(int r, int k, int K) { return
 __host__ __device__ __forceinline__ uint32_t canon32(int r, int k, int K) { return (uint32_t)(((r >> 3) * (K >> 2) + (k >> 2)) * 128 + (r & 7) * 16 + (k & 3) * 4); }
 
 // instruction descriptor: c = f32 (bit 4), a = b = bf16 (bits 7, 10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+// general form: c format (0 = f16, 1 = f32) at [4,6), a / b format (0 = f16, 1 = bf16, 2 = tf32) at [7,10) / [10,13)
+__host__ __device__ constexpr uint32_t idesc_any(int N, uint32_t cfmt, uint32_t afmt, uint32_t bfmt)
+{
+    return (cfmt << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+}
 // tf32 operands: format code 2 at bits [7,10) and [10,13)
 __host__ __device__ constexpr uint32_t idesc_tf32(int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24); }
 __host__ __device__ constexpr uint32_t idesc(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24); }
@@ -187,6 +195,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+// 32 columns of 16-bit accumulators (one f16 per column) -> 16 registers of f16x2 pairs (column 2c low, 2c+1 high)
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.pack::16b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t relu_f16x2(uint32_t x)
+{
+    uint32_t r;
+    // relu(x * 1 + (-0)) == relu(x): HFMA2.RELU runs on the FMA pipe, which this kernel leaves idle, instead of the
+    // ALU pipe (HMNMX2) that the conversion and env warps compete for
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3C003C00u), "r"(0x80008000u));
+    return r;
+}
+__device__ __forceinline__ uint16_t f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -238,13 +265,15 @@ __device__ __forceinline__ uint32_t tf32_relu_bits(float x)
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
-// x = hi + mid + lo with each piece exactly representable in bf16
+// x = hi + mid + lo with each piece exactly representable in bf16 (or f16)
+template <bool F16 = false>
 __device__ __forceinline__ void split3(float x, float& hi, float& mid, float& lo)
 {
-    hi = bf16_round(x);
+    hi = F16 ? f16_round(x) : bf16_round(x);
     const float r1 = __fadd_rn(x, -hi);
-    mid = bf16_round(r1);
-    lo = bf16_round(__fadd_rn(r1, -mid));
+    mid = F16 ? f16_round(r1) : bf16_round(r1);
+    const float r2 = __fadd_rn(r1, -mid);
+    lo = F16 ? f16_round(r2) : bf16_round(r2);
 }
 
 struct Args {
@@ -262,8 +291,11 @@ struct Args {
 //   k: 0 z1h 1 z1m 2 z1l 3 z1h 4 z1m 5 z1h | 6 z2h 7 z2m 8 z2l 9 z2h 10 z2m 11 z2h | 12 inv/2 13 inv/2 | 14 1 15 1
 // against B1 (stage_weights): w0h w0h w0h w0m w0m w0l | w1h w1h w1h w1m w1m w1l | w2h w2m | b1h b1m
 // ---------------------------------------------------------------------------------------------
+// F16 = true writes the same slots as f16 pieces (the operand type of the f16 mode, whose accumulators are f16)
+template <bool F16>
 __global__ void tc32_a1_kernel(int64_t T, int64_t nchunks, const BarSig* __restrict__ sig, uint8_t* __restrict__ a1)
 {
+    auto bits = [](float x) { return F16 ? f16_bits(x) : bf16_bits(x); };
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nchunks * TILE_ROWS) return;
     const int64_t c = idx / TILE_ROWS;
@@ -275,12 +307,12 @@ __global__ void tc32_a1_kernel(int64_t T, int64_t nchunks, const BarSig* __restr
     if (r < TILE_BARS * 5 && t < T) {
         const float z1 = sig[t].z1, z2 = sig[t].z2;
         float h, m, l;
-        split3(z1, h, m, l);
-        v[0] = v[3] = v[5] = bf16_bits(h); v[1] = v[4] = bf16_bits(m); v[2] = bf16_bits(l);
-        split3(z2, h, m, l);
-        v[6] = v[9] = v[11] = bf16_bits(h); v[7] = v[10] = bf16_bits(m); v[8] = bf16_bits(l);
-        v[12] = v[13] = bf16_bits((float)(r % 5 - 2) * 0.5f);            // drl_engine.py:35
-        v[14] = v[15] = bf16_bits(1.0f);
+        split3<F16>(z1, h, m, l);
+        v[0] = v[3] = v[5] = bits(h); v[1] = v[4] = bits(m); v[2] = bits(l);
+        split3<F16>(z2, h, m, l);
+        v[6] = v[9] = v[11] = bits(h); v[7] = v[10] = bits(m); v[8] = bits(l);
+        v[12] = v[13] = bits((float)(r % 5 - 2) * 0.5f);                 // drl_engine.py:35
+        v[14] = v[15] = bits(1.0f);
     }
     uint8_t* tile = a1 + c * A1_BYTES;
 #pragma unroll
@@ -294,14 +326,14 @@ __global__ void tc32_a1_kernel(int64_t T, int64_t nchunks, const BarSig* __restr
 
 // one genome element -> its slots in the B operands of individual slot g.  B1 (layer 1) is always the bf16
 // split; B2 / B3 are bf16 (K padded to 48) or tf32 (K padded to 40).
-template <bool TF32>
+template <int MODE>
 __device__ __forceinline__ void scatter_weight(Smem& sm, int g, int e, float v)
 {
-    auto put = [](uint8_t* base, uint32_t off, float x) { *reinterpret_cast<uint16_t*>(base + off) = bf16_bits(x); };
+    auto put = [](uint8_t* base, uint32_t off, float x) { *reinterpret_cast<uint16_t*>(base + off) = MODE == M_F16 ? f16_bits(x) : bf16_bits(x); };
     auto put32 = [](uint8_t* base, uint32_t off, uint32_t bits) { *reinterpret_cast<uint32_t*>(base + off) = bits; };
     if (e < 96) {                                      // W1[j, i]   (models/model.py:10)
         const int j = e / 3, i = e % 3;
-        float h, m, l; split3(v, h, m, l);
+        float h, m, l; split3<MODE == M_F16>(v, h, m, l);
         uint8_t* b = sm.b1[g];
         if (i < 2) {
             const int k0 = i * 6;
@@ -312,9 +344,19 @@ __device__ __forceinline__ void scatter_weight(Smem& sm, int g, int e, float v)
         }
     } else if (e < 128) {                              // b1[j]
         const int j = e - 96;
-        const float h = bf16_round(v), m = bf16_round(__fadd_rn(v, -h));
+        const float h = MODE == M_F16 ? f16_round(v) : bf16_round(v);
+        const float m = __fadd_rn(v, -h);                          // rounded to the operand type by put()
         put(sm.b1[g], canon(j, 14, K1), h); put(sm.b1[g], canon(j, 15, K1), m);
-    } else if (TF32) {
+    } else if (MODE == M_F16) {
+        // f16 operands in the bf16 tile geometry (K padded to 48): hi = f16(v), lo = f16(v - hi) for biases and W3
+        auto put16 = [](uint8_t* base, uint32_t off, uint16_t bits) { *reinterpret_cast<uint16_t*>(base + off) = bits; };
+        const float hf = f16_round(v);
+        const uint16_t hb = f16_bits(v), lb = f16_bits(__fadd_rn(v, -hf));
+        if (e < 1152) { put16(sm.b2[g], canon((e - 128) >> 5, (e - 128) & 31, K2), hb); }
+        else if (e < 1184) { put16(sm.b2[g], canon(e - 1152, 32, K2), hb); put16(sm.b2[g], canon(e - 1152, 33, K2), lb); }
+        else if (e < 1248) { const int o = (e - 1184) >> 5, k = (e - 1184) & 31; put16(sm.b3[g], canon(o, k, K2), hb); put16(sm.b3[g], canon(o + 2, k, K2), lb); }
+        else { const int o = e - 1248; put16(sm.b3[g], canon(o, 32, K2), hb); put16(sm.b3[g], canon(o, 33, K2), lb); }
+    } else if (MODE == M_TF32) {
         // hi = tf32(v), lo = tf32(v - hi): biases and W3 carry both, W2 only hi
         const uint32_t hb = tf32_bits(v), lb = tf32_bits(__fadd_rn(v, -__uint_as_float(hb)));
         if (e < 1152) { put32(sm.b2[g], canon32((e - 128) >> 5, (e - 128) & 31, K2T), hb); }
@@ -435,6 +477,9 @@ struct Ctx {
     uint32_t tmem_base, lane_addr;       // TMEM base; base + this warp's lane quarter
     uint32_t gt, gc;                     // units / chunks this CTA has processed before this group (phase sources)
     uint32_t nchunks, UG, nunits;        // this group: chunks, units per chunk, units
+    uint32_t nunits_p;                   // units rounded up to a multiple of NBUF (the pad units compute on stale operands and
+                                         // publish nothing): unit i of a group always lives in TMEM buffer i % NBUF, so the
+                                         // buffer is a compile-time constant of the unrolled issuer loops
     int G, lane, quarter;
     int64_t grp, T, count;
     const BarSig* sig; const BarPx* px; const uint8_t* a1;
@@ -480,10 +525,14 @@ __device__ __forceinline__ void umma_commit_a(uint32_t addr)
 }
 
 // L2 / L3 issuer: a converged warp; one elected lane issues the six MMAs of a unit and one commit
-template <int LAYER, bool TF32>
+template <int LAYER, int MODE>
 __device__ __noinline__ void issue_role(const Ctx& cx)
 {
-    constexpr uint32_t ID = TF32 ? (LAYER == 2 ? idesc_tf32(32) : idesc_tf32(16)) : (LAYER == 2 ? idesc(32) : idesc(16));
+    constexpr bool TF32 = MODE == M_TF32;
+    // layer 2 of the f16 mode accumulates in f16 (half the TMEM read traffic of the conversion); layer 3 always in fp32
+    constexpr uint32_t ID = MODE == M_TF32 ? (LAYER == 2 ? idesc_tf32(32) : idesc_tf32(16))
+                          : MODE == M_F16 ? (LAYER == 2 ? idesc_any(32, 0, 0, 0) : idesc_any(16, 1, 0, 0))
+                                          : (LAYER == 2 ? idesc(32) : idesc(16));
     constexpr uint32_t DSTEP = LAYER == 2 ? S_D : S_D3;
     constexpr uint32_t BSTEP = (uint32_t)((LAYER == 2 ? B2_BYTES : B3_BYTES) >> 4);
     constexpr uint32_t SBO = TF32 ? (K2T / 4) * 128 : (K2 / 8) * 128;           // distance between 8-row groups of the B tile
@@ -494,40 +543,42 @@ __device__ __noinline__ void issue_role(const Ctx& cx)
     const uint32_t d0 = cx.tmem_base + (LAYER == 2 ? C_R2 : C_R3), a0 = cx.tmem_base + (LAYER == 2 ? C_R1 : C_R2);
     const uint32_t one = cx.tmem_base + C_ONE;
     const uint32_t blo0 = desc_lo(cx.sm_addr + (uint32_t)(LAYER == 2 ? offsetof(Smem, b2) : offsetof(Smem, b3)), 128), bhi = desc_hi(SBO);
-    const uint32_t UG = cx.UG, nunits = cx.nunits;
+    const uint32_t UG = cx.UG, nunits_p = cx.nunits_p;
     uint32_t u = 0, blo = blo0;
-    uint32_t b = cx.gt % NBUF, par = (cx.gt / NBUF) & 1u, col = b * BUF_COLS, boff = b * 8u;
+    uint32_t par = (cx.gt / NBUF) & 1u;                                    // cx.gt is a multiple of NBUF
 #pragma unroll 1
-    for (uint32_t it = 0; it < nunits; ++it) {
-        mbar_wait_a_(cx, ready0 + boff, par);
-        if (LAYER == 2) mbar_wait_a_(cx, l3done0 + boff, par ^ 1u);        // layer 3 has read the A operand that lives where D2 goes
-        tc_fence_after();
-        if (elect_one()) {
-            const uint32_t d = d0 + col, aa = a0 + col;
+    for (uint32_t it = 0; it < nunits_p; it += NBUF, par ^= 1u) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {                                      // the two tiles of the unit
-                const uint32_t dj = d + (uint32_t)j * DSTEP, aj = aa + (uint32_t)j * S_D, bj = blo + (uint32_t)j * BSTEP;
+        for (uint32_t bi = 0; bi < NBUF; ++bi) {                           // unit it + bi lives in buffer bi: constant offsets
+            mbar_wait_a_(cx, ready0 + bi * 8u, par);
+            if (LAYER == 2) mbar_wait_a_(cx, l3done0 + bi * 8u, par ^ 1u);  // layer 3 has read the A operand that lives where D2 goes
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = d0 + bi * BUF_COLS, aa = a0 + bi * BUF_COLS;
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {                             // +8 TMEM columns and +256 B of B per K-step
-                    if (TF32) umma_ts2_tf32(dj, aj + 8u * k, bj + 16u * k, bhi, ID, k > 0 ? 1u : 0u);
-                    else umma_ts2(dj, aj + 8u * k, bj + 16u * k, bhi, ID, k > 0 ? 1u : 0u);
+                for (int j = 0; j < 2; ++j) {                                  // the two tiles of the unit
+                    const uint32_t dj = d + (uint32_t)j * DSTEP, aj = aa + (uint32_t)j * S_D, bj = blo + (uint32_t)j * BSTEP;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {                         // +8 TMEM columns and +256 B of B per K-step
+                        if (TF32) umma_ts2_tf32(dj, aj + 8u * k, bj + 16u * k, bhi, ID, k > 0 ? 1u : 0u);
+                        else umma_ts2(dj, aj + 8u * k, bj + 16u * k, bhi, ID, k > 0 ? 1u : 0u);
+                    }
+                    // bias step: A = the constant [1 1 0 ...] columns
+                    if (TF32) umma_ts2_tf32(dj, one, bj + 16u * KSTEPS, bhi, ID, 1u);
+                    else umma_ts2(dj, one, bj + 16u * KSTEPS, bhi, ID, 1u);
                 }
-                // bias step: A = the constant [1 1 0 ...] columns
-                if (TF32) umma_ts2_tf32(dj, one, bj + 16u * KSTEPS, bhi, ID, 1u);
-                else umma_ts2(dj, one, bj + 16u * KSTEPS, bhi, ID, 1u);
+                umma_commit_a(done0 + bi * 8u);
             }
-            umma_commit_a(done0 + boff);
+            __syncwarp();
+            blo += 2 * BSTEP;
+            if (++u == UG) { u = 0; blo = blo0; }
         }
-        __syncwarp();
-        b += 1; col += BUF_COLS; boff += 8u;
-        if (b == NBUF) { b = 0; col = 0; boff = 0; par ^= 1u; }
-        blo += 2 * BSTEP;
-        if (++u == UG) { u = 0; blo = blo0; }
     }
 }
 
 // L1 issuer + TMA producer of the A1 ring.  Both tiles of a unit share the A1 tile and their B1 operands are
 // adjacent in shared memory (4 row groups of 256 B each): ONE M=128, N=64, K=16 MMA fills D1 of both tiles.
+template <int MODE>
 __device__ __noinline__ void l1_role(const Ctx& cx)
 {
     const uint32_t nchunks = cx.nchunks, UG = cx.UG, nunits = cx.nunits, gc = cx.gc;
@@ -543,40 +594,63 @@ __device__ __noinline__ void l1_role(const Ctx& cx)
         __syncwarp();
     };
     for (uint32_t c = 0; c < nchunks && c < (uint32_t)(A1_STAGES - 1); ++c) load_a1(c);
-    constexpr uint32_t ID64 = idesc(64);
+    constexpr uint32_t ID64 = MODE == M_F16 ? idesc_any(64, 0, 0, 0) : idesc(64);      // f16 mode: f16 operands and accumulator
     const uint32_t b1lo0 = desc_lo(cx.sm_addr + (uint32_t)offsetof(Smem, b1), 128), dhi = desc_hi(256);
     const uint32_t l2done0 = BAR(l2_done, 0), l1done0 = BAR(l1_done, 0);
-    uint32_t c1 = 0, u1 = 0, blo = b1lo0, alo = 0;
-    uint32_t b = cx.gt % NBUF, par = (cx.gt / NBUF) & 1u, col = b * BUF_COLS, boff = b * 8u;
+    uint32_t c1 = 0, u1 = 0, blo = b1lo0, alo = 0, slot = 0;
+    uint32_t par = (cx.gt / NBUF) & 1u;
+    const uint32_t nunits_p = cx.nunits_p;
 #pragma unroll 1
-    for (uint32_t it = 0; it < nunits; ++it) {
-        const uint32_t q = gc + c1, slot = q % A1_STAGES;
-        if (u1 == 0) {
-            if (c1 + A1_STAGES - 1 < nchunks) load_a1(c1 + A1_STAGES - 1);
-            mbar_wait_a_(cx, BAR(a1_full, slot), (q / A1_STAGES) & 1u);
-            alo = desc_lo(a1_smem + slot * (uint32_t)A1_BYTES, 128);
+    for (uint32_t it = 0; it < nunits_p; it += NBUF, par ^= 1u) {
+#pragma unroll
+        for (uint32_t bi = 0; bi < NBUF; ++bi) {
+            const bool real = it + bi < nunits;                  // pad units reuse the last A1 tile and B1 pair
+            if (real && u1 == 0) {
+                const uint32_t q = gc + c1;
+                slot = q % A1_STAGES;
+                if (c1 + A1_STAGES - 1 < nchunks) load_a1(c1 + A1_STAGES - 1);
+                mbar_wait_a_(cx, BAR(a1_full, slot), (q / A1_STAGES) & 1u);
+                alo = desc_lo(a1_smem + slot * (uint32_t)A1_BYTES, 128);
+            }
+            mbar_wait_a_(cx, l2done0 + bi * 8u, par ^ 1u);        // layer 2 of the unit that used this buffer before has read its A operand
+            tc_fence_after();
+            const bool last = real && (u1 + 1 == UG);
+            if (elect_one()) {
+                umma_ss2(cx.tmem_base + C_R1 + bi * BUF_COLS, alo, dhi, blo, dhi, ID64, 0u);
+                umma_commit_a(l1done0 + bi * 8u);
+                if (last) umma_commit_a(BAR(a1_empty, slot));
+            }
+            __syncwarp();
+            if (real) {
+                if (last) { u1 = 0; ++c1; blo = b1lo0; } else { ++u1; blo += 2u * (uint32_t)(B1_BYTES >> 4); }
+            }
         }
-        mbar_wait_a_(cx, l2done0 + boff, par ^ 1u);                // layer 2 of the unit that used this buffer before has read its A operand
-        tc_fence_after();
-        const bool last = (u1 + 1 == UG);
-        if (elect_one()) {
-            umma_ss2(cx.tmem_base + C_R1 + col, alo, dhi, blo, dhi, ID64, 0u);
-            umma_commit_a(l1done0 + boff);
-            if (last) umma_commit_a(BAR(a1_empty, slot));
-        }
-        __syncwarp();
-        b += 1; col += BUF_COLS; boff += 8u;
-        if (b == NBUF) { b = 0; col = 0; boff = 0; par ^= 1u; }
-        blo += 2u * (uint32_t)(B1_BYTES >> 4);
-        if (last) { u1 = 0; ++c1; blo = b1lo0; } else ++u1;
     }
 }
 
 // accumulator (fp32, TMEM) -> ReLU -> bf16 pairs written back IN PLACE as the next layer's A operand, both tiles
 // of a unit, this warp's 32 rows
-template <bool TF32>
+template <int MODE>
 __device__ __forceinline__ void convert_unit(uint32_t addr)
 {
+    if (MODE == M_F16) {
+        // f16 accumulators (one per column): packed read of two columns per register, ReLU on f16 pairs, stored back
+        // as the f16 A operand -- no conversion instruction at all and half the TMEM read traffic
+        uint32_t h0[16], h1[16];
+        tmem_ld32_pack16(addr, h0);
+        tmem_ld32_pack16(addr + S_D, h1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h0[j] = relu_f16x2(h0[j]);
+        tmem_st16(addr, h0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h1[j] = relu_f16x2(h1[j]);
+        tmem_st16(addr + S_D, h1);
+        tmem_st_wait();
+        tc_fence_before();
+        return;
+    }
+    constexpr bool TF32 = MODE == M_TF32;
     uint32_t v0[32], v1[32];
     tmem_ld32(addr, v0);
     tmem_ld32(addr + S_D, v1);                                       // second tile of the unit
@@ -601,25 +675,25 @@ __device__ __forceinline__ void convert_unit(uint32_t addr)
 }
 
 // E12: set s (four warps) owns TMEM buffer s: for each of its units it converts D1 -> A2, then D2 -> A3
-template <bool TF32>
+template <int MODE>
 __device__ __noinline__ void convert_role(const Ctx& cx, uint32_t set)
 {
-    const uint32_t it0 = (set + NBUF - cx.gt % NBUF) % NBUF;
-    uint32_t par = ((cx.gt + it0) / NBUF) & 1u;
+    const uint32_t it0 = set;                                    // cx.gt is a multiple of NBUF: unit it lives in buffer it % NBUF
+    uint32_t par = (cx.gt / NBUF) & 1u;
     const uint32_t r1 = cx.lane_addr + C_R1 + set * BUF_COLS, r2 = cx.lane_addr + C_R2 + set * BUF_COLS;
     const uint32_t l1_done = BAR(l1_done, set), a2_ready = BAR(a2_ready, set), l2_done = BAR(l2_done, set), l3_ready = BAR(l3_ready, set);
-    const uint32_t nunits = cx.nunits;
+    const uint32_t nunits = cx.nunits_p;                         // the pad units are converted too (keeps the barrier phases in step)
     const bool leader = cx.lane == 0;
 #pragma unroll 1
     for (uint32_t it = it0; it < nunits; it += NBUF, par ^= 1u) {
         mbar_wait_a_(cx, l1_done, par);
         tc_fence_after();
-        convert_unit<TF32>(r1);
+        convert_unit<MODE>(r1);
         __syncwarp();
         if (leader) mbar_arrive_a(a2_ready);
         mbar_wait_a_(cx, l2_done, par);
         tc_fence_after();
-        convert_unit<TF32>(r2);
+        convert_unit<MODE>(r2);
         __syncwarp();
         if (leader) mbar_arrive_a(l3_ready);
     }
@@ -654,8 +728,8 @@ __device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
     };
     const uint32_t taddr = cx.lane_addr + C_R3 + e3set * BUF_COLS;
     const uint32_t l3_done = BAR(l3_done, e3set), l3_ready = BAR(l3_ready, e3set);
-    uint32_t par = ((gt + (e3set + NBUF - gt % NBUF) % NBUF) / NBUF) & 1u;       // parity of this set's first unit
-    uint32_t base3 = gt % NBUF;                                                 // (global index of the chunk's first unit) % 3
+    uint32_t par = (gt / NBUF) & 1u;                                            // cx.gt is a multiple of NBUF
+    uint32_t base3 = 0;                                                         // (index of the chunk's first unit) % 3
     const uint32_t ug3 = UG % NBUF;
     const int inv = iv - 2;
     const bool leader = lane == 0;
@@ -732,6 +806,19 @@ __device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
             if (leader) mbar_arrive_a(tab_full);
         }
     }
+    // pad units of the group (at most two, one per set): drain the accumulator so that the barrier phases stay in step
+    for (uint32_t it = cx.nunits; it < cx.nunits_p; ++it) {
+        if (it % NBUF != e3set) continue;
+        mbar_wait_a_(cx, l3_done, par);
+        tc_fence_after();
+        uint32_t v[4];
+        tmem_ld4(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (leader) mbar_arrive_a(l3_ready);
+        par ^= 1u;
+    }
 }
 
 // walker: one lane per individual of the group
@@ -779,7 +866,7 @@ __device__ __noinline__ void walker_role(const Ctx& cx)
     }
 }
 
-template <bool FEE, bool TF32>
+template <bool FEE, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -818,7 +905,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     if (warp < 4) {
         // the constant K-step shared by every layer-2 / layer-3 MMA: K slots 32, 33 = 1.0 (they meet the
         // bias rows of B2 / B3), 34..47 = 0
-        uint32_t c[8] = {TF32 ? 0x3F800000u : 0x3F803F80u, TF32 ? 0x3F800000u : 0u, 0, 0, 0, 0, 0, 0};
+        constexpr bool TF32 = MODE == M_TF32;
+        uint32_t c[8] = {TF32 ? 0x3F800000u : (MODE == M_F16 ? 0x3C003C00u : 0x3F803F80u), TF32 ? 0x3F800000u : 0u, 0, 0, 0, 0, 0, 0};
         tmem_st8(lane_addr + C_ONE, c);
         tmem_st_wait();
     }
@@ -832,6 +920,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     Ctx cx;
     cx.sm = &sm; cx.sm_addr = smem_u32(&sm); cx.tmem_base = tmem_base; cx.lane_addr = lane_addr;
     cx.gt = 0; cx.gc = 0; cx.nchunks = nchunks; cx.UG = UG; cx.nunits = nunits;
+    cx.nunits_p = (nunits + NBUF - 1) / NBUF * NBUF;
     cx.G = G; cx.lane = lane; cx.quarter = quarter; cx.T = T; cx.count = pop.count;
     cx.sig = a.sig; cx.px = a.px; cx.a1 = a.a1; cx.tick = a.tick; cx.phi = a.phi; cx.fee = a.fee;
     cx.fitness = a.fitness; cx.trades = a.trades; cx.raw_table = a.raw_table; cx.act_trace = a.act_trace;
@@ -849,7 +938,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 if (q < 312) src.at4(e0, v);
                 else { v[0] = src.at(e0); v[1] = src.at(e0 + 1); }
             }
-            if (!TF32 && e0 >= 128 && e0 < 1152) {              // 4 consecutive k of one W2 row: one 8-byte store
+            if (MODE == M_BF16 && e0 >= 128 && e0 < 1152) {     // 4 consecutive k of one W2 row: one 8-byte store
                 const int j = (e0 - 128) >> 5, k = (e0 - 128) & 31;
                 uint2 o;
                 o.x = bf16_bits(v[0]) | ((uint32_t)bf16_bits(v[1]) << 16);
@@ -857,21 +946,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 *reinterpret_cast<uint2*>(sm.b2[g] + canon(j, k, K2)) = o;
             } else {
                 const int n = q < 312 ? 4 : 2;
-                for (int i = 0; i < n; ++i) scatter_weight<TF32>(sm, g, e0 + i, v[i]);
+                for (int i = 0; i < n; ++i) scatter_weight<MODE>(sm, g, e0 + i, v[i]);
             }
         }
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
         cx.grp = grp;
-        if (warp < WARP_E3) convert_role<TF32>(cx, (uint32_t)warp >> 2);
+        if (warp < WARP_E3) convert_role<MODE>(cx, (uint32_t)warp >> 2);
         else if (warp < WARP_L1) e3_role<FEE>(cx, e3set);
-        else if (warp == WARP_L1) l1_role(cx);
-        else if (warp == WARP_L2) issue_role<2, TF32>(cx);
-        else if (warp == WARP_L3) issue_role<3, TF32>(cx);
+        else if (warp == WARP_L1) l1_role<MODE>(cx);
+        else if (warp == WARP_L2) issue_role<2, MODE>(cx);
+        else if (warp == WARP_L3) issue_role<3, MODE>(cx);
         else walker_role(cx);
 
-        cx.gt += nunits;
+        cx.gt += cx.nunits_p;
         cx.gc += nchunks;
         tc_fence_before();
         __syncthreads();                            // every role is done with this group's weights and tables
@@ -886,7 +975,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
 }  // namespace tc32
 
 int tc32_chunks(int64_t T) { return (int)((T + tc32::TILE_BARS - 1) / tc32::TILE_BARS); }
-size_t tc32_a1_bytes(int64_t T) { return (size_t)tc32_chunks(T) * tc32::A1_BYTES; }
+size_t tc32_a1_bytes(int64_t T) { return 2 * (size_t)tc32_chunks(T) * tc32::A1_BYTES; }   // bf16 tiles, then f16 tiles
 
 int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st)
 {
@@ -894,7 +983,8 @@ int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st)
     if (b->T == 0) return SGMM_OK;
     const int64_t nchunks = tc32_chunks(b->T);
     const int64_t n = nchunks * TILE_ROWS;
-    tc32_a1_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->T, nchunks, b->sig, b->a1);
+    tc32_a1_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->T, nchunks, b->sig, b->a1);
+    tc32_a1_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->T, nchunks, b->sig, b->a1 + nchunks * A1_BYTES);
     return check_cuda(cudaGetLastError(), "tc32_a1_kernel launch");
 }
 
@@ -912,13 +1002,13 @@ int tc32_group_size(int64_t count, int sms)
 }
 
 int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
-                float* raw_table, int32_t* act_trace, cudaStream_t st, bool tf32)
+                float* raw_table, int32_t* act_trace, cudaStream_t st, int mode)
 {
     using namespace tc32;
     if (mm.count == 0) return SGMM_OK;
     if (act_trace && !raw_table) { set_error("act_trace needs raw_table"); return SGMM_ERR_INVALID; }
     Args a;
-    a.sig = b->sig; a.px = b->px; a.a1 = b->a1; a.T = b->T; a.tick = b->tick; a.phi = phi; a.fee = fee;
+    a.sig = b->sig; a.px = b->px; a.a1 = b->a1 + (mode == M_F16 ? tc32_chunks(b->T) * A1_BYTES : 0); a.T = b->T; a.tick = b->tick; a.phi = phi; a.fee = fee;
     a.mm = mm; a.fitness = fitness; a.trades = trades; a.raw_table = raw_table; a.act_trace = act_trace;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
@@ -926,11 +1016,19 @@ int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee,
     const int64_t groups = (mm.count + a.group - 1) / a.group;
     const int grid = (int)(groups < sms ? groups : sms);
     const size_t smem = sizeof(Smem) + 128;
-    static bool configured[4] = {false, false, false, false};
+    static bool configured[6] = {false, false, false, false, false, false};
     const bool has_fee = fee != 0.0;
-    const int variant = (has_fee ? 1 : 0) | (tf32 ? 2 : 0);
-    auto kern = tf32 ? (has_fee ? tc32_kernel<true, true> : tc32_kernel<false, true>)
-                     : (has_fee ? tc32_kernel<true, false> : tc32_kernel<false, false>);
+    if (mode < 0 || mode > 2) { set_error("unknown tensor-core mode %d", mode); return SGMM_ERR_INVALID; }
+    const int variant = (has_fee ? 1 : 0) + 2 * mode;
+    void (*kern)(const Args) = nullptr;
+    switch (variant) {
+        case 0: kern = tc32_kernel<false, M_BF16>; break;
+        case 1: kern = tc32_kernel<true, M_BF16>; break;
+        case 2: kern = tc32_kernel<false, M_TF32>; break;
+        case 3: kern = tc32_kernel<true, M_TF32>; break;
+        case 4: kern = tc32_kernel<false, M_F16>; break;
+        default: kern = tc32_kernel<true, M_F16>; break;
+    }
     if (!configured[variant]) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(tc32 smem)")) return rc;

@@ -29,7 +29,7 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-PRECISION_F32, PRECISION_BF16, PRECISION_TF32 = 0, 1, 2
+PRECISION_F32, PRECISION_BF16, PRECISION_TF32, PRECISION_F16 = 0, 1, 2, 3
 
 
 def _precision(precision, hidden):
@@ -43,6 +43,8 @@ def _precision(precision, hidden):
         return PRECISION_BF16
     if precision in ("tf32", PRECISION_TF32):
         return PRECISION_TF32
+    if precision in ("f16", "fp16", PRECISION_F16):
+        return PRECISION_F16
     raise ValueError(f"unknown precision {precision!r}")
 
 

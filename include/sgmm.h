@@ -55,6 +55,9 @@ extern "C" {
                                     /* activations in TMEM rounded to 10 mantissa bits, tf32 weights):    */
                                     /* ~4x tighter policy outputs at ~equal speed                        */
 
+#define SGMM_PRECISION_F16   3      /* H=32 only: f16 operands AND f16 accumulators for layers 1-2 (read back  */
+                                    /* packed, ReLU on f16 pairs, no conversion), fp32 for layer 3             */
+
 /* rollout flags */
 #define SGMM_FLAG_NONE       0
 

@@ -15,7 +15,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 # stated tolerance on raw*5 (ticks) for offsets spanning +-10 ticks, per precision; the measured maximum is printed
-TAU = {"bf16": 0.12, "tf32": 0.03}
+TAU = {"bf16": 0.12, "tf32": 0.03, "f16": 0.03}
 TAU_TICKS = TAU["bf16"]
 
 
@@ -58,7 +58,7 @@ def _audit(orc, bz, genomes, raw, T, TAU_TICKS=TAU_TICKS):
     return worst, flips_outside
 
 
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "f16"])
 @pytest.mark.parametrize("fee", [0.0, 3e-4])
 def test_policy_outputs_within_tolerance_and_env_bit_exact(sg, orc, fee, precision):
     TAU_TICKS = TAU[precision]
@@ -133,7 +133,7 @@ def test_seeded_children_match_explicit_genomes(sg, orc):
     assert torch.equal(f_exp, f_seed) and torch.equal(t_exp, t_seed)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "f16"])
 def test_golden_arl_checkpoint_audit_set(sg, orc, precision):
     """The fixed audit set: the reference's shipped ARL agent on its own 960-bar test bundle (tests/golden,
     960/960 recorded actions).  On the (bar, inventory) pairs the recorded run visited, the tensor-core

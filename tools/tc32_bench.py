@@ -13,7 +13,7 @@ bun = sgmm_b200.Bundle.from_arrays(bundle, synthetic.train_stats_of(bundle), 0.0
 master, genomes = synthetic.policy_like_genomes(P, hidden=32, seed=0, out_scale=6.0, out_bias=(0.1, 0.1))
 g = torch.from_numpy(genomes).cuda()
 out = {"P": P, "T": bun.T}
-for prec in ("bf16", "tf32", "f32"):
+for prec in ("f16", "bf16", "tf32", "f32"):
     def run():
         return sgmm_b200.rollout_population(bun, g, phi=1e-4, precision=prec, units_per_lane=group if prec != "f32" else 0)
     for _ in range(2):
