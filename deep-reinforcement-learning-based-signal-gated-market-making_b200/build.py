@@ -46,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs
+    extra = os.environ.get("SGMM_EXTRA_NVCC_FLAGS", "").split()      # debug builds, e.g. -DSGMM_TC32_WATCHDOG / -DSGMM_SPEC256_TRACE
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-shared", "-o", LIB] + srcs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "csrc", "build.log")
     with open(log, "w") as f:

@@ -35,6 +35,8 @@
 // rounding flips where the oracle's margin exceeds it, and checks that GIVEN the kernel's actions
 // every integer and fp64 quantity is bit-identical to the oracle (teacher-forced replay).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cstdio>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
 #include "sgmm_step_core.h"
@@ -42,6 +44,11 @@
 namespace sgmm {
 
 namespace s256 {
+#ifdef SGMM_SPEC256_TRACE
+#define TR(ev) do { if (blockIdx.x == 0 && gt == 0 && it >= 64 && it < 72 && lane == 0) sm.trace[it - 64][ev] = clock64(); } while (0)
+#else
+#define TR(ev) do { } while (0)
+#endif
 
 constexpr int H = 256;
 constexpr int TILE_ROWS = 128;
@@ -57,26 +64,55 @@ constexpr uint32_t C_D3 = 128;                // D3 lives in columns 128..143 of
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int64_t G = (int64_t)H * H + 7 * H + 2;       // 67330
 
-struct __align__(32) TableEntry {
-    double reward;          // reward of taking this row's action from this inventory (market_env.py:58)
-    int32_t ka, kb;         // quantised offsets (drl_engine.py:39)
-    int32_t next;           // inventory index (inv+2) after the step
-    int32_t traded;         // 1 if any side filled (drl_engine.py:60-61)
-    float raw_a, raw_b;     // policy outputs (audit)
-};
+// One 25-bar tile of the walk through the table (the same two-phase walk as sgmm_tc32.cu):
+//   phase A: the 5-state automaton alone -- a 2-instruction chain per bar (byte `w` of the bar's 8-byte record:
+//            next | traded << 3), its loads independent of the chain;
+//   phase B: rewards of the visited rows summed in the reference's order (drl_engine.py:54): loads independent of the
+//            running sum, only the fp64 add chain is serial.
+// (A walk that chased one 32-byte entry per bar -- load, then the next address from the loaded inventory -- cost 170
+//  cycles per bar and was THE bottleneck of this kernel: 4 200 of the tile's 4 200 cycles, profiles/r1_spec256_trace.txt.)
+template <bool FULL>
+__device__ __forceinline__ void walk_tile(const uint8_t* nb, const double* rb, int n, int& iv, int& trades, double& total)
+{
+    uint32_t es[TILE_BARS], ivs[TILE_BARS];
+    uint32_t w = (uint32_t)iv;
+#pragma unroll
+    for (int s = 0; s < TILE_BARS; ++s) {
+        ivs[s] = w; es[s] = 0;
+        if (FULL || s < n) {
+            const uint2 x = *reinterpret_cast<const uint2*>(nb + s * 8);
+            es[s] = __byte_perm(x.x, x.y, w);
+            w = es[s] & 7u;
+        }
+    }
+    iv = (int)w;
+#pragma unroll
+    for (int s = 0; s < TILE_BARS; ++s) {
+        if (FULL || s < n) {
+            trades += (int)(es[s] & 8u);                                          // drl_engine.py:60-61 (x8; divided out by the caller)
+            total = add_rn(total, rb[s * 5 + ivs[s]]);
+        }
+    }
+}
 
 struct Smem {
     uint8_t b_tile[NKB][H * 128];              // W2 bf16, [k-block][n][64] swizzled, 128 KB
     uint8_t a_tile[NKB][TILE_ROWS * 128];      // h1 bf16, [k-block][row][64] swizzled, 64 KB
     uint8_t b3_tile[B3_BYTES];                 // layer-3 B operand (no swizzle: 8 x 16-byte core matrices)
     float w1x[H], w1y[H], w1i[H], b1[H], b2[H];
+    uint32_t b2h[H / 2];                       // b2 as f16 pairs (F16 build: added by the epilogue's HFMA2.RELU)
     float b3[4];
-    TableEntry table[2][TILE_ROWS];
+    double tab_r[2][TILE_ROWS];                // reward of (bar, inventory) rows (market_env.py:58)
+    alignas(8) uint8_t tab_n[2][TILE_BARS * 8]; // next inventory index | traded << 3, 8 bytes per bar
+    int32_t tab_k[2][TILE_ROWS][2];            // quantised offsets of the row (audit: act_trace)
     // d_full: L2 committed (D2 complete); a3_ready: E2 wrote A3; l3_done: L3 committed (D3 complete);
     // d_empty: E3 has read D3, the buffer may take the next D2
     uint64_t a_full[NKB], a_empty[NKB], d_full[2], a3_ready[2], l3_done[2], d_empty[2], t_full[2], t_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
+#ifdef SGMM_SPEC256_TRACE
+    long long trace[8][16];
+#endif
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,7 +149,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit 4), a=b=bf16 (bits 7,10), K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+// F16 = true: f16 operands and an F16 accumulator for layer 2 (c format 0, a/b format 0).  One f16 per TMEM column,
+// read back two columns per register (.pack::16b): half the tensor-memory read traffic of the epilogue, bias + ReLU in
+// ONE HFMA2.RELU per pair and no conversion; f16 keeps 11 significand bits against bf16's 8.  Layer 3 accumulates in fp32.
+constexpr bool F16 = true;
+constexpr uint32_t IDESC = (F16 ? 0u : ((1u << 4) | (1u << 7) | (1u << 10))) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
 
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
 {
@@ -125,7 +165,7 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
 }
 // layer 3: A operand from tensor memory, B (no swizzle) from shared memory, N = 16
-constexpr uint32_t IDESC_L3 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+constexpr uint32_t IDESC_L3 = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate)
 {
     asm volatile(
@@ -181,16 +221,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // two fp32 -> packed bf16x2 with ReLU; `lo` lands in the low half (lower address)
-__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi)        // (operand type of the build: bf16 or f16)
 {
     uint32_t r;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
     uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    if (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float op_round(float x) { return F16 ? __half2float(__float2half_rn(x)) : bf16_round(x); }
+__device__ __forceinline__ uint16_t op_bits(float x) { return F16 ? __half_as_ushort(__float2half_rn(x)) : bf16_bits(x); }
+// 32 columns of 16-bit accumulators -> 16 registers of f16x2 pairs (column 2c low, 2c+1 high)
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.pack::16b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t bias_relu_f16x2(uint32_t x, uint32_t b)  // relu(x * 1 + b) on f16 pairs (HFMA2.RELU)
+{
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3C003C00u), "r"(b));
     return r;
 }
 // byte offset of 16-byte chunk `c` (8 bf16) of row `r` inside a [rows][128 B] SWIZZLE_128B slab
@@ -265,12 +324,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 sm.b1[j] = src.at(3 * H + j);
                 sm.b2[j] = src.at(4 * H + (int64_t)H * H + j);
             }
+            for (int j = tid; j < H / 2; j += NUM_THREADS)
+                sm.b2h[j] = pack_bf16(src.at(4 * H + (int64_t)H * H + 2 * j), src.at(4 * H + (int64_t)H * H + 2 * j + 1));
             for (int q = tid; q < 2 * H; q += NUM_THREADS) {                  // W3[o, k]: row o = bf16(w), row o+2 = bf16 residual
                 const int o = q / H, k = q % H;
                 const float w = src.at(5 * H + (int64_t)H * H + q);
-                const float h = bf16_round(w), m = bf16_round(__fadd_rn(w, -h));
-                *reinterpret_cast<uint16_t*>(&sm.b3_tile[canon(o, k, H)]) = bf16_bits(h);
-                *reinterpret_cast<uint16_t*>(&sm.b3_tile[canon(o + 2, k, H)]) = bf16_bits(m);
+                const float h = op_round(w), m = op_round(__fadd_rn(w, -h));
+                *reinterpret_cast<uint16_t*>(&sm.b3_tile[canon(o, k, H)]) = op_bits(h);
+                *reinterpret_cast<uint16_t*>(&sm.b3_tile[canon(o + 2, k, H)]) = op_bits(m);
             }
             if (tid < 2) sm.b3[tid] = src.at(7 * H + (int64_t)H * H + tid);
         }
@@ -287,30 +348,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
                 mbar_wait(&sm.d_full[buf], use & 1u);
                 tc_fence_after();
+                if (warp == 0) TR(3);
                 const uint32_t tbase = lane_addr + buf * 256u;
-                uint32_t v[2][32];
-                tmem_ld32(tbase, v[0]);
+                if (F16) {
+                    uint32_t h[2][16];
+                    tmem_ld32_pack16(tbase, h[0]);
 #pragma unroll
-                for (int cc = 0; cc < H / 32; ++cc) {
-                    tmem_ld_wait();                                        // chunk cc has landed
-                    if (cc + 1 < H / 32) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
-                    const uint32_t* w = v[cc & 1];
-                    uint32_t p[16];
+                    for (int cc = 0; cc < H / 32; ++cc) {
+                        tmem_ld_wait();                                    // chunk cc has landed
+                        if (cc + 1 < H / 32) tmem_ld32_pack16(tbase + (uint32_t)((cc + 1) * 32), h[(cc + 1) & 1]);   // prefetch
+                        const uint32_t* w = h[cc & 1];
+                        uint32_t p[16];
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cc * 32 + c]);
-                        const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(w[c]), __uint_as_float(w[c + 1])), make_float2(bb.x, bb.y));
-                        const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(w[c + 2]), __uint_as_float(w[c + 3])), make_float2(bb.z, bb.w));
-                        p[c >> 1] = pack_relu_bf16(x0.x, x0.y);
-                        p[(c >> 1) + 1] = pack_relu_bf16(x1.x, x1.y);
+                        for (int c = 0; c < 16; c += 4) {
+                            const uint4 bb = *reinterpret_cast<const uint4*>(&sm.b2h[cc * 16 + c]);
+                            p[c] = bias_relu_f16x2(w[c], bb.x); p[c + 1] = bias_relu_f16x2(w[c + 1], bb.y);
+                            p[c + 2] = bias_relu_f16x2(w[c + 2], bb.z); p[c + 3] = bias_relu_f16x2(w[c + 3], bb.w);
+                        }
+                        tmem_st16(tbase + (uint32_t)(cc * 16), p);        // writes trail reads (see below)
                     }
-                    // columns 16cc..16cc+15 were read (as part of chunk cc/2) before they are overwritten: writes trail reads
-                    tmem_st16(tbase + (uint32_t)(cc * 16), p);
+                } else {
+                    uint32_t v[2][32];
+                    tmem_ld32(tbase, v[0]);
+#pragma unroll
+                    for (int cc = 0; cc < H / 32; ++cc) {
+                        tmem_ld_wait();                                        // chunk cc has landed
+                        if (cc + 1 < H / 32) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);   // prefetch
+                        const uint32_t* w = v[cc & 1];
+                        uint32_t p[16];
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cc * 32 + c]);
+                            const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(w[c]), __uint_as_float(w[c + 1])), make_float2(bb.x, bb.y));
+                            const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(w[c + 2]), __uint_as_float(w[c + 3])), make_float2(bb.z, bb.w));
+                            p[c >> 1] = pack_relu_bf16(x0.x, x0.y);
+                            p[(c >> 1) + 1] = pack_relu_bf16(x1.x, x1.y);
+                        }
+                        // columns 16cc..16cc+15 were read (as part of chunk cc/2) before they are overwritten: writes trail reads
+                        tmem_st16(tbase + (uint32_t)(cc * 16), p);
+                    }
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.a3_ready[buf]);
+                if (warp == 0) TR(4);
             };
             auto e3 = [&](int64_t it) {                    // D3 -> offsets -> speculative env step -> table
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
@@ -326,19 +408,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 }
                 mbar_wait(&sm.l3_done[buf], use & 1u);
                 tc_fence_after();
+                if (warp == 0) TR(5);
                 uint32_t v[4];
                 tmem_ld4(lane_addr + buf * 256u + C_D3, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.d_empty[buf]);                // the buffer may take the next D2
+                if (warp == 0) TR(6);
                 const float ra = __fadd_rn(__fadd_rn(__uint_as_float(v[0]), __uint_as_float(v[2])), sm.b3[0]);   // W3 hi + lo, + b3
                 const float rb = __fadd_rn(__fadd_rn(__uint_as_float(v[1]), __uint_as_float(v[3])), sm.b3[1]);
                 const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));          // drl_engine.py:39
                 const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
                 // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                TableEntry e;
-                e.ka = ka; e.kb = kb; e.raw_a = ra; e.raw_b = rb; e.reward = 0.0; e.next = iv; e.traded = 0;
+                double reward = 0.0; uint32_t nxt = (uint32_t)iv;
                 if (valid) {
                     const int inv = iv - 2;
                     const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
@@ -355,9 +438,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                     pnl = fs ? add_rn(pnl, leg_s) : pnl;
                     const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
                     const int ai = ninv < 0 ? -ninv : ninv;
-                    e.reward = sub_rn(pnl, mul_rn(a.phi, (double)ai));        // :57-58
-                    e.next = ninv + 2;
-                    e.traded = (fb || fs) ? 1 : 0;
+                    reward = sub_rn(pnl, mul_rn(a.phi, (double)ai));         // :57-58
+                    nxt = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);     // drl_engine.py:60-61
                     if (a.raw_table) {
                         float* o = a.raw_table + (((int64_t)ind * T + t) * 5 + iv) * 2;
                         o[0] = ra; o[1] = rb;
@@ -365,9 +447,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 }
                 // publish the tile's table
                 mbar_wait(&sm.t_empty[buf], (use & 1u) ^ 1u);
-                sm.table[buf][row] = e;
+                if (row < TILE_BARS * 5) {
+                    sm.tab_r[buf][row] = reward;
+                    sm.tab_n[buf][tl * 8 + iv] = (uint8_t)nxt;
+                    if (a.act_trace) { sm.tab_k[buf][row][0] = ka; sm.tab_k[buf][row][1] = kb; }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.t_full[buf]);
+                if (warp == 0) TR(7);
             };
             for (int64_t it = 0; it < ntiles; ++it) {
                 if (it > 0) e3(it - 1);
@@ -409,6 +496,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 }
                 // the slot: wait until the MMAs of the previous tile have consumed it
                 if (g > 0) mbar_wait(&sm.a_empty[kb], (g - 1) & 1u);
+                if (pw == 0) TR(9);
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     const int tlm = (gtid >> 3) + 8 * m;
@@ -435,6 +523,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.a_full[kb]);
+                if (pw == 0) TR(10);
             }
         } else if (warp == WARP_MMA) {
             // =========================== L2 ISSUER (converged warp, one elected lane issues) ===========
@@ -442,10 +531,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
                 mbar_wait(&sm.d_empty[buf], (use & 1u) ^ 1u);              // E3 has read the D3 that lived in this buffer
                 tc_fence_after();
+                TR(0);
                 const uint32_t d = tmem_base + buf * 256u;
                 for (int kb = 0; kb < NKB; ++kb) {
                     mbar_wait(&sm.a_full[kb], g & 1u);
                     tc_fence_after();
+                    if (kb == 0) TR(1);
+                    if (kb == NKB - 1) TR(2);
                     if (elect_one()) {
                         const uint64_t ad = make_desc(smem_u32(&sm.a_tile[kb][0]));
                         const uint64_t bd = make_desc(smem_u32(&sm.b_tile[kb][0]));
@@ -465,6 +557,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
                 mbar_wait(&sm.a3_ready[buf], use & 1u);
                 tc_fence_after();
+                TR(8);
                 if (elect_one()) {
                     const uint32_t base = tmem_base + buf * 256u;
 #pragma unroll
@@ -482,26 +575,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 for (int64_t it = 0; it < ntiles; ++it) {
                     const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
                     mbar_wait(&sm.t_full[buf], use & 1u);
+                    TR(11);
                     const int64_t t0 = it * TILE_BARS;
                     const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
-                    for (int s = 0; s < n; ++s) {
-                        const TableEntry& e = sm.table[buf][s * 5 + iv];
-                        total = add_rn(total, e.reward);                      // drl_engine.py:54
-                        trades += e.traded;
-                        if (a.act_trace) { a.act_trace[((int64_t)ind * T + t0 + s) * 2] = e.ka; a.act_trace[((int64_t)ind * T + t0 + s) * 2 + 1] = e.kb; }
-                        iv = e.next;
+                    const uint8_t* nb = sm.tab_n[buf];
+                    const double* rbp = sm.tab_r[buf];
+                    if (n == TILE_BARS && !a.act_trace) walk_tile<true>(nb, rbp, n, iv, trades, total);      // every tile but the last
+                    else {
+                        int w = iv;
+                        walk_tile<false>(nb, rbp, n, iv, trades, total);
+                        if (a.act_trace) {                                    // audit: the offsets taken (second pass over the automaton)
+                            for (int s = 0; s < n; ++s) {
+                                int32_t* at = a.act_trace + ((int64_t)ind * T + t0 + s) * 2;
+                                at[0] = sm.tab_k[buf][s * 5 + w][0]; at[1] = sm.tab_k[buf][s * 5 + w][1];
+                                w = nb[s * 8 + w] & 7;
+                            }
+                        }
                     }
                     mbar_arrive(&sm.t_empty[buf]);
                 }
+                trades >>= 3;                                                 // walk_tile counts in units of 8
                 if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
                 a.fitness[ind] = total; a.trades[ind] = trades;
             }
             __syncwarp();
         }
-        gt += (uint32_t)ntiles;
         tc_fence_before();
         __syncthreads();                            // every role is done with this individual's weights
         tc_fence_after();
+#ifdef SGMM_SPEC256_TRACE
+        if (blockIdx.x == 0 && gt == 0 && tid == 0 && ntiles >= 72) {
+            const long long t00 = sm.trace[0][0];
+            for (int i = 0; i < 8; ++i) {
+                printf("tile %d:", 64 + i);
+                for (int e = 0; e < 12; ++e) printf(" e%d=%lld", e, sm.trace[i][e] - t00);
+                printf("\n");
+            }
+        }
+#endif
+        gt += (uint32_t)ntiles;
     }
 
     if (warp == WARP_MMA) {
