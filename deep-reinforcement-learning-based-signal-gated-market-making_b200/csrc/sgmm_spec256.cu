@@ -249,6 +249,12 @@ __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[1
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c)   // relu(a * b + c) on f16 pairs
+{
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ uint32_t bias_relu_f16x2(uint32_t x, uint32_t b)  // relu(x * 1 + b) on f16 pairs (HFMA2.RELU)
 {
     uint32_t r;
@@ -485,6 +491,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const float4 s0 = *reinterpret_cast<const float4*>(&sm.b1[k0]), s1 = *reinterpret_cast<const float4*>(&sm.b1[k0 + 4]);
                 bb[0] = make_float2(s0.x, s0.y); bb[1] = make_float2(s0.z, s0.w); bb[2] = make_float2(s1.x, s1.y); bb[3] = make_float2(s1.z, s1.w);
             }
+            uint32_t wih[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) wih[p] = pack_bf16(wi[p].x, wi[p].y);
             uint8_t* slab = &sm.a_tile[kb][0];
             for (int64_t it = 0; it < ntiles; ++it) {
                 const uint32_t g = gt + (uint32_t)it;
@@ -508,18 +517,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
 #pragma unroll
                         for (int p = 0; p < 4; ++p)          // SGMM-F32 layer 1: b1, +W1[.,0] z1, +W1[.,1] z2
                             A[p] = __ffma2_rn(wy[p], make_float2(z[m].y, z[m].y), __ffma2_rn(wx[p], make_float2(z[m].x, z[m].x), bb[p]));
+                        if (F16) {
+                            // the bar part of layer 1 stays in fp32 (SGMM order) and is rounded ONCE to f16 pairs; the
+                            // inventory term and the ReLU are one HFMA2.RELU per pair and row: no per-row conversion
+                            // (cvt.rn.relu.f16x2.f32 per row kept the XU pipe at 129 %)
+                            uint32_t Ah[4];
 #pragma unroll
-                        for (int iv = 0; iv < 5; ++iv) {
-                            const float inv2 = (float)(iv - 2) * 0.5f;       // drl_engine.py:35
-                            uint4 o;
-                            float2 v0 = __ffma2_rn(wi[0], make_float2(inv2, inv2), A[0]);
-                            float2 v1 = __ffma2_rn(wi[1], make_float2(inv2, inv2), A[1]);
-                            float2 v2 = __ffma2_rn(wi[2], make_float2(inv2, inv2), A[2]);
-                            float2 v3 = __ffma2_rn(wi[3], make_float2(inv2, inv2), A[3]);
-                            o.x = pack_relu_bf16(v0.x, v0.y); o.y = pack_relu_bf16(v1.x, v1.y);
-                            o.z = pack_relu_bf16(v2.x, v2.y); o.w = pack_relu_bf16(v3.x, v3.y);
-                            const int r = tlm * 5 + iv;
-                            *reinterpret_cast<uint4*>(slab + swz(r, c)) = o;
+                            for (int p = 0; p < 4; ++p) Ah[p] = pack_bf16(A[p].x, A[p].y);
+#pragma unroll
+                            for (int iv = 0; iv < 5; ++iv) {
+                                // inv / 2 as an f16 pair (drl_engine.py:35): -1, -0.5, 0, 0.5, 1
+                                const uint32_t i2 = iv == 0 ? 0xBC00BC00u : iv == 1 ? 0xB800B800u : iv == 2 ? 0u : iv == 3 ? 0x38003800u : 0x3C003C00u;
+                                uint4 o;
+                                o.x = hfma2_relu(wih[0], i2, Ah[0]); o.y = hfma2_relu(wih[1], i2, Ah[1]);
+                                o.z = hfma2_relu(wih[2], i2, Ah[2]); o.w = hfma2_relu(wih[3], i2, Ah[3]);
+                                const int r = tlm * 5 + iv;
+                                *reinterpret_cast<uint4*>(slab + swz(r, c)) = o;
+                            }
+                        } else {
+    #pragma unroll
+                            for (int iv = 0; iv < 5; ++iv) {
+                                const float inv2 = (float)(iv - 2) * 0.5f;       // drl_engine.py:35
+                                uint4 o;
+                                float2 v0 = __ffma2_rn(wi[0], make_float2(inv2, inv2), A[0]);
+                                float2 v1 = __ffma2_rn(wi[1], make_float2(inv2, inv2), A[1]);
+                                float2 v2 = __ffma2_rn(wi[2], make_float2(inv2, inv2), A[2]);
+                                float2 v3 = __ffma2_rn(wi[3], make_float2(inv2, inv2), A[3]);
+                                o.x = pack_relu_bf16(v0.x, v0.y); o.y = pack_relu_bf16(v1.x, v1.y);
+                                o.z = pack_relu_bf16(v2.x, v2.y); o.w = pack_relu_bf16(v3.x, v3.y);
+                                const int r = tlm * 5 + iv;
+                                *reinterpret_cast<uint4*>(slab + swz(r, c)) = o;
+                            }
                         }
                     }
                 }
@@ -535,8 +563,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
             // next tile, finished only when that tile did, and the buffer hand-back E3 -> d_empty -> next layer 2 left
             // the tensor pipe idle for ~400 cycles per tile: profiles/r1_spec256_trace.txt.)
             const uint64_t bd0 = make_desc_ns(smem_u32(sm.b3_tile), 128, (H / 8) * 128);
-            auto issue_l3 = [&](int64_t it3) {                               // D3[128,16] = A3 (TMEM) x B3^T
-                const uint32_t g3 = gt + (uint32_t)it3, buf3 = g3 & 1u, use3 = g3 >> 1;
+            auto issue_l3 = [&](int64_t it) {                               // D3[128,16] = A3 (TMEM) x B3^T
+                const uint32_t g3 = gt + (uint32_t)it, buf3 = g3 & 1u, use3 = g3 >> 1;
                 mbar_wait(&sm.a3_ready[buf3], use3 & 1u);
                 tc_fence_after();
                 TR(8);
