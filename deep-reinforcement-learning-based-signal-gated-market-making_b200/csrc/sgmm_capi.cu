@@ -167,7 +167,7 @@ int sgmm_bundle_destroy(sgmm_bundle* b)
     if (!b) return SGMM_OK;
     {
         DeviceGuard guard(b->device);
-        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->a1); cudaFree(b->ws);
+        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->a1); cudaFree(b->ws); cudaFree(b->codes);
     }
     delete b;
     return SGMM_OK;

@@ -41,6 +41,10 @@ struct sgmm_bundle {
     std::mutex ws_mutex;
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // [count][T] 64-bit step codes of the tensor-core rollouts (sgmm_account.cu), grow-only
+    std::mutex codes_mutex;
+    uint64_t* codes = nullptr;
+    size_t codes_cap = 0;
 };
 
 namespace sgmm {
@@ -84,6 +88,9 @@ int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee,
                 float* raw_table, int32_t* act_trace, cudaStream_t st, int mode = 0);   // mode: 0 bf16, 1 tf32, 2 f16
 inline int tc32_mode_of(int precision) { return precision == SGMM_PRECISION_TF32 ? 1 : (precision == SGMM_PRECISION_F16 ? 2 : 0); }
 int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st);
+int launch_account(const sgmm_bundle* b, const uint64_t* codes, int64_t count, double phi, double fee, double* fitness,
+                   int32_t* trades, cudaStream_t st);
+int reserve_codes(const sgmm_bundle* b, int64_t count, cudaStream_t st, uint64_t** out);
 size_t tc32_a1_bytes(int64_t T);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,
                     const double* ask, const double* bid, cudaStream_t st);

@@ -70,32 +70,28 @@ constexpr int64_t G = (int64_t)H * H + 7 * H + 2;       // 67330
 // One 25-bar tile of the walk through the table (the same two-phase walk as sgmm_tc32.cu):
 //   phase A: the 5-state automaton alone -- a 2-instruction chain per bar (byte `w` of the bar's 8-byte record:
 //            next | traded << 3), its loads independent of the chain;
-//   phase B: rewards of the visited rows summed in the reference's order (drl_engine.py:54): loads independent of the
-//            running sum, only the fp64 add chain is serial.
+//   phase B: the step codes of the visited rows go to global memory in bar order; the fp64 accounting (rewards,
+//            reference-order sum, trade count) is sgmm_account.cu's, AFTER this kernel: an FP64 instruction issued
+//            while tcgen05.mma executes waits ~740 cycles instead of 9 (tools/walk_bench.cu).
 // (A walk that chased one 32-byte entry per bar -- load, then the next address from the loaded inventory -- cost 170
 //  cycles per bar and was THE bottleneck of this kernel: 4 200 of the tile's 4 200 cycles, profiles/r1_spec256_trace.txt.)
 template <bool FULL>
-__device__ __forceinline__ void walk_tile(const uint8_t* nb, const double* rb, int n, int& iv, int& trades, double& total)
+__device__ __forceinline__ void walk_tile(const uint8_t* nb, const uint64_t* cb, int n, int& iv, uint64_t* out)
 {
-    uint32_t es[TILE_BARS], ivs[TILE_BARS];
+    uint32_t ivs[TILE_BARS];
     uint32_t w = (uint32_t)iv;
 #pragma unroll
     for (int s = 0; s < TILE_BARS; ++s) {
-        ivs[s] = w; es[s] = 0;
+        ivs[s] = w;
         if (FULL || s < n) {
             const uint2 x = *reinterpret_cast<const uint2*>(nb + s * 8);
-            es[s] = __byte_perm(x.x, x.y, w);
-            w = es[s] & 7u;
+            w = __byte_perm(x.x, x.y, w) & 7u;
         }
     }
     iv = (int)w;
 #pragma unroll
-    for (int s = 0; s < TILE_BARS; ++s) {
-        if (FULL || s < n) {
-            trades += (int)(es[s] & 8u);                                          // drl_engine.py:60-61 (x8; divided out by the caller)
-            total = add_rn(total, rb[s * 5 + ivs[s]]);
-        }
-    }
+    for (int s = 0; s < TILE_BARS; ++s)
+        if (FULL || s < n) __stcs(out + s, cb[s * 5 + ivs[s]]);          // the visited row's step code (sgmm_account.cu)
 }
 
 struct Smem {
@@ -105,7 +101,7 @@ struct Smem {
     float w1x[H], w1y[H], w1i[H], b1[H], b2[H];
     uint32_t b2h[H / 2];                       // b2 as f16 pairs (F16 build: added by the epilogue's HFMA2.RELU)
     float b3[4];
-    double tab_r[2][TILE_ROWS];                // reward of (bar, inventory) rows (market_env.py:58)
+    uint64_t tab_c[2][TILE_ROWS];              // step code of (bar, inventory) rows: offsets, fills, |inv'| (sgmm_account.cu)
     alignas(8) uint8_t tab_n[2][TILE_BARS * 8]; // next inventory index | traded << 3, 8 bytes per bar
     int32_t tab_k[2][TILE_ROWS][2];            // quantised offsets of the row (audit: act_trace)
     // d_full: L2 committed (D2 complete); a3_ready: E2 wrote A3; l3_done: L3 committed (D3 complete);
@@ -265,7 +261,7 @@ __device__ __forceinline__ uint32_t bias_relu_f16x2(uint32_t x, uint32_t b)  // 
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 struct Args {
-    const BarSig* sig; const BarPx* px; int64_t T;
+    const BarSig* sig; const BarPx* px; uint64_t* codes; int64_t T;
     double tick, phi, fee;
     PopArgs mm;
     double* fitness; int32_t* trades;
@@ -409,12 +405,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const int64_t t = it * TILE_BARS + tl;
                 const bool valid = (row < TILE_BARS * 5) && (t < T);
                 const int64_t tc_ = valid ? t : 0;
-                int2 kth = make_int2(0, 0); double2 ab = make_double2(0., 0.); double mid = 0.0;
-                if (T > 0) {
-                    kth = __ldg(reinterpret_cast<const int2*>(&a.sig[tc_].ka1));
-                    ab = __ldg(reinterpret_cast<const double2*>(&a.px[tc_].ask));
-                    mid = __ldg(&a.px[tc_].mid_next);
-                }
+                int2 kth = make_int2(0, 0);
+                if (T > 0) kth = __ldg(reinterpret_cast<const int2*>(&a.sig[tc_].ka1));
                 mbar_wait(&sm.l3_done[buf], use & 1u);
                 tc_fence_after();
                 if (warp == 0) TR(5);
@@ -430,34 +422,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                 const int ka = __float2int_rn(__fmul_rn(ra, 5.0f));          // drl_engine.py:39
                 const int kb = __float2int_rn(__fmul_rn(rb, 5.0f));
                 // speculative env step of (bar t, inventory iv-2)  (market_env.py:30-58)
-                double reward = 0.0; uint32_t nxt = (uint32_t)iv;
+                uint64_t code = 0; uint32_t nxt = (uint32_t)iv;
                 if (valid) {
+                    // the INTEGER half of the env step (market_env.py:34-38, 45, 51); quotes, P&L and the penalty are
+                    // fp64 and belong to the accounting pass
                     const int inv = iv - 2;
                     const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
                     const bool fs = (inv > -2) && (ka < kth.x);              // :35,:38
-                    const double my_ask = add_rn(ab.x, mul_rn((double)ka, a.tick));
-                    const double my_bid = sub_rn(ab.y, mul_rn((double)kb, a.tick));
-                    double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
-                    if (FEE) {
-                        leg_b = sub_rn(leg_b, mul_rn(my_bid, a.fee));
-                        leg_s = sub_rn(leg_s, mul_rn(my_ask, a.fee));
-                    }
-                    double pnl = 0.0;
-                    pnl = fb ? add_rn(pnl, leg_b) : pnl;
-                    pnl = fs ? add_rn(pnl, leg_s) : pnl;
                     const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
                     const int ai = ninv < 0 ? -ninv : ninv;
-                    reward = sub_rn(pnl, mul_rn(a.phi, (double)ai));         // :57-58
-                    nxt = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);     // drl_engine.py:60-61
+                    const int kac = max(min(ka, (1 << 23) - 1), -(1 << 23)), kbc = max(min(kb, (1 << 23) - 1), -(1 << 23));
+                    code = (uint64_t)((uint32_t)kac & 0xFFFFFFu) | ((uint64_t)((uint32_t)kbc & 0xFFFFFFu) << 24) |
+                           ((uint64_t)(fb ? 1u : 0u) << 48) | ((uint64_t)(fs ? 1u : 0u) << 49) | ((uint64_t)ai << 50);
+                    nxt = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
                     if (a.raw_table) {
                         float* o = a.raw_table + (((int64_t)ind * T + t) * 5 + iv) * 2;
                         o[0] = ra; o[1] = rb;
                     }
                 }
                 // publish the tile's table
+                if (warp == 0) TR(13);
                 mbar_wait(&sm.t_empty[buf], (use & 1u) ^ 1u);
+                if (warp == 0) TR(14);
                 if (row < TILE_BARS * 5) {
-                    sm.tab_r[buf][row] = reward;
+                    sm.tab_c[buf][row] = code;
                     sm.tab_n[buf][tl * 8 + iv] = (uint8_t)nxt;
                     if (a.act_trace) { sm.tab_k[buf][row][0] = ka; sm.tab_k[buf][row][1] = kb; }
                 }
@@ -605,8 +593,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
         } else {
             // =========================== WALKER ================================================
             if (lane == 0) {
-                int iv = 2, trades = 0;                                       // inventory 0
-                double total = 0.0;                                           // drl_engine.py:26
+                int iv = 2;                                                   // inventory 0
+                uint64_t* codes = a.codes + (int64_t)ind * T;
                 for (int64_t it = 0; it < ntiles; ++it) {
                     const uint32_t g = gt + (uint32_t)it, buf = g & 1u, use = g >> 1;
                     mbar_wait(&sm.t_full[buf], use & 1u);
@@ -614,11 +602,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                     const int64_t t0 = it * TILE_BARS;
                     const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
                     const uint8_t* nb = sm.tab_n[buf];
-                    const double* rbp = sm.tab_r[buf];
-                    if (n == TILE_BARS && !a.act_trace) walk_tile<true>(nb, rbp, n, iv, trades, total);      // every tile but the last
+                    if (n == TILE_BARS && !a.act_trace) walk_tile<true>(nb, sm.tab_c[buf], n, iv, codes + t0);      // every tile but the last
                     else {
                         int w = iv;
-                        walk_tile<false>(nb, rbp, n, iv, trades, total);
+                        walk_tile<false>(nb, sm.tab_c[buf], n, iv, codes + t0);
                         if (a.act_trace) {                                    // audit: the offsets taken (second pass over the automaton)
                             for (int s = 0; s < n; ++s) {
                                 int32_t* at = a.act_trace + ((int64_t)ind * T + t0 + s) * 2;
@@ -627,11 +614,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                             }
                         }
                     }
+                    TR(12);
                     mbar_arrive(&sm.t_empty[buf]);
                 }
-                trades >>= 3;                                                 // walk_tile counts in units of 8
-                if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
-                a.fitness[ind] = total; a.trades[ind] = trades;
             }
             __syncwarp();
         }
@@ -643,7 +628,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
             const long long t00 = sm.trace[0][0];
             for (int i = 0; i < 8; ++i) {
                 printf("tile %d:", 64 + i);
-                for (int e = 0; e < 12; ++e) printf(" e%d=%lld", e, sm.trace[i][e] - t00);
+                for (int e = 0; e < 15; ++e) printf(" e%d=%lld", e, sm.trace[i][e] - t00);
                 printf("\n");
             }
         }
@@ -666,6 +651,7 @@ int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double f
     Args a;
     a.sig = b->sig; a.px = b->px; a.T = b->T; a.tick = b->tick; a.phi = phi; a.fee = fee;
     a.mm = mm; a.fitness = fitness; a.trades = trades; a.raw_table = raw_table; a.act_trace = act_trace;
+    if (int rc = reserve_codes(b, mm.count, st, &a.codes)) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
     const int grid = (int)(mm.count < sms ? mm.count : sms);
@@ -679,7 +665,8 @@ int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double f
         configured[has_fee] = true;
     }
     kern<<<grid, NUM_THREADS, smem, st>>>(a);
-    return check_cuda(cudaGetLastError(), "spec256_kernel launch");
+    if (int rc = check_cuda(cudaGetLastError(), "spec256_kernel launch")) return rc;
+    return launch_account(b, a.codes, mm.count, phi, fee, fitness, trades, st);     // the fp64 half, after the tensor-core kernel
 }
 
 }  // namespace sgmm
