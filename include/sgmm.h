@@ -47,7 +47,14 @@ extern "C" {
                                     /*   H=32  all three layers as GEMMs chained through TMEM         */
                                     /*         (sgmm_tc32.cu; params.units_per_lane = individuals per */
                                     /*         CTA group, even, 0 = auto)                             */
-                                    /*   H=256 hidden layer (sgmm_spec256.cu)                         */
+                                    /*   H=256 hidden and output layer (sgmm_spec256.cu: f16 operands,*/
+                                    /*         f16 layer-2 accumulator, whatever tensor mode is asked;*/
+                                    /*         the rollout kernel records 64-bit step codes in a      */
+                                    /*         grow-only scratch buffer OF THE BUNDLE and a second    */
+                                    /*         kernel does the fp64 accounting: H=256 rollouts on one */
+                                    /*         bundle must be ordered on one stream, and the first    */
+                                    /*         rollout of a given size must not run under a stream    */
+                                    /*         capture (it allocates); offsets saturate at +-2^23)    */
                                     /* policy outputs within a stated tolerance of the fp32 oracle;   */
                                     /* the env step given the offsets stays bit-exact                 */
 

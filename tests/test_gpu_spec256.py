@@ -1,5 +1,6 @@
-"""GPU (-m gpu): the H=256 tensor-core path (tcgen05, bf16 inputs, fp32 accumulate in TMEM;
-BASELINE.json config 4).  Parity is stated in two halves:
+"""GPU (-m gpu): the H=256 tensor-core path (tcgen05; f16 operands, f16 layer-2 accumulator in TMEM, fp32 output layer;
+BASELINE.json config 4).  The rollout kernel does the integer half of the env step and records 64-bit step codes; the
+fp64 accounting is a second kernel (sgmm_account.cu).  Parity is stated in two halves:
 
   (1) POLICY OUTPUTS vs the fp32 oracle (SGMM-F32 order, oracle/sgmm_oracle.c) for EVERY (bar,
       inventory) pair: |d(raw*5)| <= TAU_TICKS, and the rounded offsets are identical wherever the
@@ -14,7 +15,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TAU_TICKS = 0.05          # stated bf16 tolerance on raw*5 (ticks); measured max is ~1e-2
+TAU_TICKS = 0.05          # stated tolerance on raw*5 (ticks); measured max is 0.008 (f16), 0.025 with bf16 operands
 
 
 @pytest.fixture(scope="module")
@@ -83,6 +84,22 @@ def test_ragged_lengths_and_many_individuals(sg, orc, T):
     for i in range(0, P, max(1, P // 7)):
         fo, to = orc.rollout(None, None, bz, 1e-4, 0.001, 0.0, forced_actions=act[i])
         assert fo == fit[i] and to == trd[i]
+
+
+@pytest.mark.parametrize("out_scale,fee", [(300.0, 0.0), (40000.0, 3e-4)])
+def test_large_offsets_through_the_step_codes(sg, orc, out_scale, fee):
+    """Offsets of hundreds to tens of thousands of ticks (both signs, both sides filling in one bar): the 24-bit offset
+    fields of the step code and the accounting kernel reproduce the oracle's env bit for bit on the kernel's actions."""
+    bundle, bz, bun, genomes = _setup(sg, orc, 1, 93, 9, seed=3, T=333, out_scale=out_scale)
+    fit, trd, raw, act = sg.rollout_spec256_audit(bun, genomes, phi=1e-4, fee_rate=fee)
+    fit, trd, act = fit.cpu().numpy(), trd.cpu().numpy(), act.cpu().numpy()
+    assert np.abs(act).max() > 50 * out_scale / 300.0          # the case is what it claims to be
+    both = 0
+    for i in range(genomes.shape[0]):
+        fo, to, tro = orc.rollout(None, None, bz, 1e-4, 0.001, fee, forced_actions=act[i], trace=True)
+        assert fo == fit[i] and to == trd[i], (i, fo, fit[i], to, trd[i])
+        both += int(np.sum(tro["fill_buy"] & tro["fill_sell"])) if "fill_buy" in tro else 0
+    print("bars with both sides filled:", both)
 
 
 def test_closed_loop_diverges_from_fp32_oracle_only_at_near_ties(sg, orc):

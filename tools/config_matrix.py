@@ -35,6 +35,8 @@ for P in (50, 2048, 4096, 8192, 16384):
         "tensor tf32 explicit": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, precision="tf32"),
         "tensor tf32 explicit+fee": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, fee_rate=3e-4, precision="tf32"),
         "tensor tf32 seeded": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4, precision="tf32"),
+        "tensor f16 explicit": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, precision="f16"),
+        "tensor f16 seeded": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4, precision="f16"),
         "tensor bf16 explicit": lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4, precision="bf16"),
         "tensor bf16 seeded": lambda: sgmm_b200.rollout_seeded(bun, m, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4, precision="bf16"),
     }
@@ -42,4 +44,13 @@ for P in (50, 2048, 4096, 8192, 16384):
         ms = timed(fn)
         rows.append({"P": P, "T": T, "case": name, "ms": round(ms, 3), "G_env_steps_per_s": round(P * T / ms / 1e6, 3)})
         print(rows[-1], flush=True)
+# BASELINE config 4 at its full size: H = 256, with fee, population 16384 (seeded children), 120 synthetic days
+bundle4 = synthetic.synthetic_bundle(120)
+bun4 = sgmm_b200.Bundle.from_arrays(bundle4, synthetic.train_stats_of(bundle4), 0.001)
+m256, _ = synthetic.policy_like_genomes(1, hidden=256, seed=0)
+m256 = torch.from_numpy(m256).cuda()
+for P in (16384,):
+    ms = timed(lambda: sgmm_b200.rollout_seeded(bun4, m256, count=P, sigma=0.05, seed=1, generation=0, phi=1e-4, fee_rate=3e-4, hidden=256), reps=2)
+    rows.append({"P": P, "T": bun4.T, "case": "config 4: H=256 tensor cores, fee, seeded", "ms": round(ms, 3), "G_env_steps_per_s": round(P * bun4.T / ms / 1e6, 3)})
+    print(rows[-1], flush=True)
 json.dump(rows, open("gpurun_out/config_matrix_r1b.json", "w"), indent=1)

@@ -87,6 +87,23 @@ __global__ void __launch_bounds__(320, 1) walk_under_load(int mma, int fg, int t
 #pragma unroll 4
                 for (int k = 0; k < 100; ++k) p = (p ^ (p >> 3)) + k;
             iv = (int)p;
+        } else if (fg == 6 || fg == 7) {                         // 100 x (tcgen05.ld.x32 + wait [+ tcgen05.st.x16 + wait]) on columns 384..
+            uint32_t r[32];
+            const uint32_t la = tb + 384u;                       // warp 0: lanes 0..31
+            for (int it = 0; it < tiles; ++it)
+                for (int k = 0; k < 100; ++k) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(la) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (fg == 7) {
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                            ::"r"(la), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    }
+                    iv += (int)(r[0] & 1u);
+                }
         } else if (fg == 5) {                                    // 100 independent conflict-free STS.128
             uint4 v = make_uint4(lane, 1, 2, 3);
             for (int it = 0; it < tiles; ++it)
@@ -111,7 +128,7 @@ __global__ void __launch_bounds__(320, 1) walk_under_load(int mma, int fg, int t
                                      ::"r"(tb), "r"(tb + 256u + (uint32_t)((i & 3) * 8)), "l"(bd + (uint64_t)((i & 3) * 2)), "r"(idesc), "r"(1u) : "memory");
                     else
                         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                                     ::"r"(tb + (uint32_t)((i & 1) * 256)), "l"(ad + (uint64_t)((i & 3) * 2)), "l"(bd + (uint64_t)((i & 3) * 2)), "r"(idesc), "r"(1u) : "memory");
+                                     ::"r"(tb), "l"(ad + (uint64_t)((i & 3) * 2)), "l"(bd + (uint64_t)((i & 3) * 2)), "r"(idesc), "r"(1u) : "memory");
                 }
             }
         }
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(32, 1) walk_kernel(int variant, int tiles, lon
     const long long t1 = clock64();
     if (lane == 0) { out[variant] = (t1 - t0) / tiles; sink[variant] = total + trades + iv; }
 }
-int main()
+int main(int argc, char** argv)
 {
     long long* d; double* s; cudaMalloc(&d, 128); cudaMalloc(&s, 128);
     cudaFuncSetAttribute(walk_under_load, cudaFuncAttributeMaxDynamicSharedMemorySize, 49 * 1024);
@@ -173,8 +190,8 @@ int main()
     long long h[3]; cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
     printf("cycles per 25-bar tile: two-phase one lane %lld, two-phase 32 lanes %lld, entry chasing (rolled) %lld\n", h[0], h[1], h[2]);
     const char* nm[] = {"idle SM", "SS N=256 MMAs back to back", "8 warps of FFMA2", "8 warps of HFMA2", "TS N=256 MMAs (A in TMEM)", "SS N=128 MMAs", "SS N=64 MMAs"};
-    const char* fn[] = {"two-phase walk of a tile (one lane)", "100 dependent LDS", "100 dependent SHFL", "100 dependent DADD", "100 dependent LOP+IADD", "100 STS.128"};
-    for (int f = 0; f < 6; ++f)
+    const char* fn[] = {"two-phase walk of a tile (one lane)", "100 dependent LDS", "100 dependent SHFL", "100 dependent DADD", "100 dependent LOP+IADD", "100 STS.128", "100 x (tcgen05.ld.x32 + wait)", "100 x (ld.x32 + wait + st.x16 + wait)"};
+    for (int f = (argc > 1 ? 6 : 0); f < 8; ++f)
         for (int m = 0; m < 7; ++m) {
             walk_under_load<<<1, 320, 49 * 1024>>>(m, f, 50, d, s);
             cudaError_t e = cudaDeviceSynchronize();
