@@ -6,7 +6,11 @@
 // reference's accounting is fp64 by definition (Env/market_env.py:30-58, Env/drl_engine.py:54), so the tensor-core
 // kernels do only the INTEGER half of the env step (offsets, fills, inventory) and record, per bar actually visited,
 // a 64-bit code; this kernel turns the codes into rewards and sums them in the reference's order:
-//     code = ka (24 bit, signed) | kb (24 bit, signed) << 24 | fill_buy << 48 | fill_sell << 49 | |inv'| << 50
+//     code = (fill_sell ? off_a : SGMM_CODE_NOFILL) | (fill_buy ? off_b : SGMM_CODE_NOFILL) << 32      (two int32)
+// (an offset is only needed on a side that filled; the inventory is re-derived here as the running sum of the fills).
+// The exact H=32 kernel uses the same split (FFMA2 and FP64 instructions share a half-rate pipe, and the int -> fp64
+// conversions sit on the XU pipe): at P = 4096 x 14 400 bars its step loop went from 5.25 ms with the fp64 accounting
+// inside to 4.79 ms writing codes (4.42 with neither), and this kernel takes 0.32 ms.
 // One warp per individual: 32 bars' rewards in parallel (un-fused fp64 in the reference's op order), then the
 // running sum bar by bar through shuffles (the only serial part: one DADD per bar).
 #include "sgmm_internal.h"
@@ -16,73 +20,114 @@ namespace sgmm {
 
 namespace {
 
-constexpr int ACCOUNT_WARPS = 4;
+// A CTA accounts ACC_IND individuals.  Warp w < ACC_IND turns the codes of 32 consecutive bars of individual w into
+// rewards (lane = bar; coalesced code loads; the fp64 legs only on lanes whose bar traded) and puts them into a
+// shared-memory tile; the last warp is the summing warp: its lane j adds individual j's 32 rewards in bar order
+// (drl_engine.py:54) -- the only serial part, 32 individuals' chains side by side in one instruction stream --
+// while the other warps already work on the next 32 bars (two tiles).
+constexpr int ACC_IND = 4;                                       // small CTAs: 4096 individuals spread evenly over 148 SMs
+constexpr int ACC_THREADS = (ACC_IND + 1) * 32;
+constexpr int ACC_STRIDE = 33;                                   // doubles per tile row: conflict-free column reads
 
-template <bool FEE>
-__global__ void __launch_bounds__(ACCOUNT_WARPS * 32) account_kernel(const uint64_t* __restrict__ codes, const BarPx* __restrict__ px,
-                                                                     int64_t T, int64_t count, double tick, double phi, double fee,
-                                                                     double* __restrict__ fitness, int32_t* __restrict__ trades)
+template <bool FEE, bool FLT>
+__global__ void __launch_bounds__(ACC_THREADS) account_kernel(const uint64_t* __restrict__ codes, const BarPx* __restrict__ px,
+                                                              int64_t T, int64_t count, double tick, double phi, double fee,
+                                                              double* __restrict__ fitness, int32_t* __restrict__ trades)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t ind = (int64_t)blockIdx.x * ACCOUNT_WARPS + (threadIdx.x >> 5);
-    if (ind >= count) return;
-    const uint64_t* c = codes + ind * T;
-    double total = 0.0;                                              // drl_engine.py:26
-    int ntr = 0;
-    for (int64_t t0 = 0; t0 < T; t0 += 32) {
-        const int64_t t = t0 + lane;
-        const bool valid = t < T;
-        double rew = 0.0;
-        bool traded = false;
-        if (valid) {
-            const uint64_t code = __ldcs(c + t);
-            const int ka = ((int)(uint32_t)(code << 8)) >> 8;                          // sign-extend 24 bits
-            const int kb = ((int)(uint32_t)((code >> 24) << 8)) >> 8;
-            const bool fb = (code >> 48) & 1u, fs = (code >> 49) & 1u;
-            const int ai = (int)((code >> 50) & 3u);
-            const double2 ab = __ldg(reinterpret_cast<const double2*>(&px[t].ask));
-            const double mid = __ldg(&px[t].mid_next);
-            const double my_ask = add_rn(ab.x, mul_rn((double)ka, tick));               // market_env.py:30
-            const double my_bid = sub_rn(ab.y, mul_rn((double)kb, tick));               // :31
-            double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
-            if (FEE) {
-                leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                             // :46,:48
-                leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                             // :52,:54
-            }
-            double pnl = 0.0;                                                           // :40
-            pnl = fb ? add_rn(pnl, leg_b) : pnl;
-            pnl = fs ? add_rn(pnl, leg_s) : pnl;
-            rew = sub_rn(pnl, mul_rn(phi, (double)ai));                                 // :57-58
-            traded = fb || fs;
-        }
-        ntr += __popc(__ballot_sync(0xffffffffu, traded));                              // drl_engine.py:60-61
-        const int n = (int)(T - t0 < 32 ? T - t0 : 32);
-        const int rlo = __double2loint(rew), rhi = __double2hiint(rew);
-        if (n == 32) {
+    __shared__ double tile[2][ACC_IND][ACC_STRIDE];
+    __shared__ int s_trades[ACC_IND];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ind0 = (int64_t)blockIdx.x * ACC_IND;
+    const int64_t nwin = (T + 31) / 32;
+    if (warp < ACC_IND) {
+        // ---------------- rewards of individual ind0 + warp, 32 bars per window ----------------
+        const int64_t ind = ind0 + warp;
+        const bool live = ind < count;
+        const uint64_t* c = codes + (live ? ind : 0) * T;
+        int ntr = 0, inv = 0;                                        // market_env.py:17 (reset)
+        const double pen0 = mul_rn(phi, 0.0), pen1 = mul_rn(phi, 1.0), pen2 = mul_rn(phi, 2.0);
+        const uint64_t none = FLT ? 0xFFFFFFFFFFFFFFFFull : 0x8000000080000000ull;            // no fills beyond T
+        uint64_t code_n = (live && lane < T) ? __ldcs(c + lane) : none;                       // window 0
+        for (int64_t w = 0; w < nwin; ++w) {
+            const int64_t t = w * 32 + lane;
+            const uint64_t code = code_n;
+            const int64_t tn = t + 32;
+            code_n = (live && tn < T) ? __ldcs(c + tn) : none;                                   // prefetch the next window
+            int ka = (int)(uint32_t)code, kb = (int)(uint32_t)(code >> 32);
+            const bool fs = ka != (FLT ? SGMM_CODE_NOFILL_F : SGMM_CODE_NOFILL), fb = kb != (FLT ? SGMM_CODE_NOFILL_F : SGMM_CODE_NOFILL);
+            if (FLT) { ka = __float2int_rn(__int_as_float(ka)); kb = __float2int_rn(__int_as_float(kb)); }   // drl_engine.py:39
+            // inventory after each bar = running sum of the fills (market_env.py:45,51)
+            int d = (fb ? 1 : 0) - (fs ? 1 : 0);
 #pragma unroll
-            for (int s = 0; s < 32; ++s)
-                total = add_rn(total, __hiloint2double(__shfl_sync(0xffffffffu, rhi, s), __shfl_sync(0xffffffffu, rlo, s)));   // drl_engine.py:54
-        } else {
-            for (int s = 0; s < n; ++s)
-                total = add_rn(total, __hiloint2double(__shfl_sync(0xffffffffu, rhi, s), __shfl_sync(0xffffffffu, rlo, s)));
+            for (int m = 1; m < 32; m <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, d, m);
+                if (lane >= m) d += o;
+            }
+            const int ninv = inv + d;
+            inv = __shfl_sync(0xffffffffu, ninv, 31);
+            const bool traded = fb || fs;
+            ntr += __popc(__ballot_sync(0xffffffffu, traded));                          // drl_engine.py:60-61
+            const int ai = ninv < 0 ? -ninv : ninv;
+            double pnl = 0.0;                                                           // market_env.py:40
+            if (traded) {
+                const double2 ab = __ldg(reinterpret_cast<const double2*>(&px[t].ask));
+                const double mid = __ldg(&px[t].mid_next);
+                if (fb) {
+                    const double my_bid = sub_rn(ab.y, mul_rn((double)kb, tick));       // :31
+                    double leg_b = sub_rn(mid, my_bid);
+                    if (FEE) leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                // :46,:48
+                    pnl = add_rn(pnl, leg_b);
+                }
+                if (fs) {
+                    const double my_ask = add_rn(ab.x, mul_rn((double)ka, tick));       // :30
+                    double leg_s = sub_rn(my_ask, mid);
+                    if (FEE) leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                // :52,:54
+                    pnl = add_rn(pnl, leg_s);
+                }
+            }
+            const double pen = ai == 0 ? pen0 : (ai == 1 ? pen1 : pen2);                 // :57
+            tile[w & 1][warp][lane] = sub_rn(pnl, pen);                                 // :58
+            __syncthreads();                                                            // tile w complete; tile w-1 consumed
         }
-    }
-    if (lane == 0) {
-        if (ntr == 0) total = sub_rn(total, 50.0);                                      // drl_engine.py:64-65
-        fitness[ind] = total;
-        trades[ind] = ntr;
+        if (lane == 0) s_trades[warp] = ntr;
+        __syncthreads();
+    } else {
+        // ---------------- the summing warp: lane j <-> individual ind0 + j ----------------
+        double total = 0.0;                                                             // drl_engine.py:26
+        const int j = lane < ACC_IND ? lane : 0;
+        for (int64_t w = 0; w < nwin; ++w) {
+            __syncthreads();
+            const int n = (int)(T - w * 32 < 32 ? T - w * 32 : 32);
+            const double* row = tile[w & 1][j];
+            if (n == 32) {
+#pragma unroll
+                for (int s = 0; s < 32; ++s) total = add_rn(total, row[s]);             // drl_engine.py:54
+            } else {
+                for (int s = 0; s < n; ++s) total = add_rn(total, row[s]);
+            }
+        }
+        __syncthreads();
+        const int64_t ind = ind0 + lane;
+        if (lane < ACC_IND && ind < count) {
+            const int ntr = s_trades[lane];
+            if (ntr == 0) total = sub_rn(total, 50.0);                                  // drl_engine.py:64-65
+            fitness[ind] = total;
+            trades[ind] = ntr;
+        }
     }
 }
 
 }  // namespace
 
 int launch_account(const sgmm_bundle* b, const uint64_t* codes, int64_t count, double phi, double fee, double* fitness,
-                   int32_t* trades, cudaStream_t st)
+                   int32_t* trades, cudaStream_t st, bool float_offsets)
 {
     if (count == 0) return SGMM_OK;
-    const unsigned grid = (unsigned)((count + ACCOUNT_WARPS - 1) / ACCOUNT_WARPS);
-    if (fee != 0.0) account_kernel<true><<<grid, ACCOUNT_WARPS * 32, 0, st>>>(codes, b->px, b->T, count, b->tick, phi, fee, fitness, trades);
-    else account_kernel<false><<<grid, ACCOUNT_WARPS * 32, 0, st>>>(codes, b->px, b->T, count, b->tick, phi, fee, fitness, trades);
+    const unsigned grid = (unsigned)((count + ACC_IND - 1) / ACC_IND);
+    void (*kern)(const uint64_t*, const BarPx*, int64_t, int64_t, double, double, double, double*, int32_t*) =
+        fee != 0.0 ? (float_offsets ? account_kernel<true, true> : account_kernel<true, false>)
+                   : (float_offsets ? account_kernel<false, true> : account_kernel<false, false>);
+    kern<<<grid, ACC_THREADS, 0, st>>>(codes, b->px, b->T, count, b->tick, phi, fee, fitness, trades);
     return check_cuda(cudaGetLastError(), "account_kernel launch");
 }
 
@@ -101,9 +146,12 @@ int reserve_codes(const sgmm_bundle* cb, int64_t count, cudaStream_t st, uint64_
                       "the stream capture first", b->codes_cap, want);
             return SGMM_ERR_INVALID;
         }
-        if (b->codes) { cudaDeviceSynchronize(); cudaFree(b->codes); b->codes = nullptr; b->codes_cap = 0; }
-        if (int rc = check_cuda(cudaMalloc(&b->codes, want * sizeof(uint64_t)), "cudaMalloc(code buffer)")) return rc;
-        b->codes_cap = want;
+        // the old buffer stays alive until the bundle is destroyed: a captured CUDA graph may hold its address
+        if (b->codes) b->codes_retired.push_back(b->codes);
+        b->codes = nullptr; b->codes_cap = 0;
+        const size_t grow = want + want / 4;
+        if (int rc = check_cuda(cudaMalloc(&b->codes, grow * sizeof(uint64_t)), "cudaMalloc(code buffer)")) return rc;
+        b->codes_cap = grow;
     }
     *out = b->codes;
     return SGMM_OK;

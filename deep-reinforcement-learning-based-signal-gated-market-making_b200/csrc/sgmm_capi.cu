@@ -168,6 +168,7 @@ int sgmm_bundle_destroy(sgmm_bundle* b)
     {
         DeviceGuard guard(b->device);
         cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->a1); cudaFree(b->ws); cudaFree(b->codes);
+        for (uint64_t* p : b->codes_retired) cudaFree(p);
     }
     delete b;
     return SGMM_OK;

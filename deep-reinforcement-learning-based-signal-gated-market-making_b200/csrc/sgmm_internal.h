@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <mutex>
+#include <vector>
 #include "../../include/sgmm.h"
 
 namespace sgmm {
@@ -21,6 +22,9 @@ struct __align__(32) BarPx {
     double ask, bid, mid_next, pad;
 };
 
+// step code of the deferred fp64 accounting (sgmm_account.cu): this value in an offset field = that side did not fill
+#define SGMM_CODE_NOFILL INT32_MIN
+#define SGMM_CODE_NOFILL_F ((int)0xFFFFFFFF)     // the same marker when the field carries the fp32 q = raw*5 (a NaN)
 constexpr int32_t K_NEVER = INT32_MIN;
 constexpr int32_t K_ALWAYS = INT32_MAX;
 constexpr int32_t K_CLAMP = 1 << 30;
@@ -45,6 +49,7 @@ struct sgmm_bundle {
     std::mutex codes_mutex;
     uint64_t* codes = nullptr;
     size_t codes_cap = 0;
+    std::vector<uint64_t*> codes_retired;
 };
 
 namespace sgmm {
@@ -71,6 +76,7 @@ struct RolloutArgs {
     PopArgs mm, adv;
     double* fitness;
     int32_t* trades;
+    uint64_t* codes;     // [count][T] step codes (sgmm_account.cu)
 };
 
 void set_error(const char* fmt, ...);
@@ -89,7 +95,7 @@ int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee,
 inline int tc32_mode_of(int precision) { return precision == SGMM_PRECISION_TF32 ? 1 : (precision == SGMM_PRECISION_F16 ? 2 : 0); }
 int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st);
 int launch_account(const sgmm_bundle* b, const uint64_t* codes, int64_t count, double phi, double fee, double* fitness,
-                   int32_t* trades, cudaStream_t st);
+                   int32_t* trades, cudaStream_t st, bool float_offsets = false);
 int reserve_codes(const sgmm_bundle* b, int64_t count, cudaStream_t st, uint64_t** out);
 size_t tc32_a1_bytes(int64_t T);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,

@@ -17,8 +17,10 @@
 //     L2 -> shared memory with cp.async.bulk (TMA 1-D bulk copies) completing on mbarriers; warps
 //     release a stage through an "empty" mbarrier and a dedicated producer warp refills it;
 //   * the env step is branch-free: fills are integer compares against per-bar thresholds derived
-//     once per bundle with the reference's exact fp64 expression, inventory/trades are integers,
-//     quotes / P&L / reward sum are un-fused fp64 in the reference's order.
+//     once per bundle with the reference's exact fp64 expression, inventory is an integer;
+//   * quotes / P&L / penalty / reward sum -- un-fused fp64 in the reference's order -- are NOT in this
+//     kernel: it records a 64-bit step code per bar and sgmm_account.cu does the fp64 half afterwards
+//     (measured at P = 4096 x 14 400 bars: 5.25 ms with the accounting in the loop, 4.79 + 0.32 ms split).
 #include <cstdio>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
@@ -189,7 +191,6 @@ struct RingSmem {
     uint64_t full[RING_STAGES];
     uint64_t empty[RING_STAGES];
     BarSig sig[RING_STAGES][CHUNK_BARS];
-    BarPx px[RING_STAGES][CHUNK_BARS];
     float hbuf[MAX_WARPS][128];          // per warp: U individuals x 32 activations, 16-B interleaved
     float rbuf[MAX_WARPS][80];           // per warp: 4 individuals x 8 lanes x (pa,pb), group stride 20 words
 };
@@ -231,9 +232,8 @@ rollout_kernel_h32(const RolloutArgs a)
                 if (c >= RING_STAGES) mbar_wait(&sm.empty[s], (uint32_t)(((c / RING_STAGES) - 1) & 1));
                 const int64_t t0 = c * CHUNK_BARS;
                 const uint32_t n = (uint32_t)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
-                mbar_arrive_expect_tx(&sm.full[s], n * (uint32_t)(sizeof(BarSig) + sizeof(BarPx)));
+                mbar_arrive_expect_tx(&sm.full[s], n * (uint32_t)sizeof(BarSig));      // (prices are the accounting pass's)
                 tma_bulk_g2s(&sm.sig[s][0], a.sig + t0, n * (uint32_t)sizeof(BarSig), &sm.full[s]);
-                tma_bulk_g2s(&sm.px[s][0], a.px + t0, n * (uint32_t)sizeof(BarPx), &sm.full[s]);
             }
         }
         return;
@@ -289,36 +289,15 @@ rollout_kernel_h32(const RolloutArgs a)
 
     float* hb = &sm.hbuf[warp][0];
     float* rbw = &sm.rbuf[warp][0];
-    const double tick = a.tick, fee = a.fee;
-    const double pen0 = mul_rn(a.phi, 0.0), pen1 = mul_rn(a.phi, 1.0), pen2 = mul_rn(a.phi, 2.0);   // market_env.py:57
-
-    int inv = 0, trades = 0, fbp = 0, fsp = 0;
+    int inv = 0, fbp = 0, fsp = 0;
     float inv2 = 0.0f;                                               // inventory / 2.0 (drl_engine.py:35), exact
-    double total = 0.0;                                              // drl_engine.py:26
 
-    // Software pipeline: the fp64 accounting of bar i-1 (quotes, P&L legs, penalty, reward sum) is
-    // issued inside step i, where the scheduler can bury its latency under the hidden-layer FMAs; only
-    // the fill decision and the inventory update stay on the step-to-step critical path.
-    // The initial pending record is an exact no-op (no fill, |inv| = 0: total += +0.0).
-    int pk_a = 0, pk_b = 0, p_ai = 0; bool p_fb = false, p_fs = false;
-
-#define SGMM_ACCOUNT(PX)                                                                              \
-    {                                                                                                 \
-        const double2 ab_ = *reinterpret_cast<const double2*>(&(PX).ask);                             \
-        const double mid_ = (PX).mid_next;                                                            \
-        const double my_ask_ = add_rn(ab_.x, mul_rn((double)pk_a, tick));       /* market_env.py:30 */ \
-        const double my_bid_ = sub_rn(ab_.y, mul_rn((double)pk_b, tick));       /* :31 */              \
-        double leg_b_ = sub_rn(mid_, my_bid_), leg_s_ = sub_rn(my_ask_, mid_);                        \
-        if (FEE) {                                                                                    \
-            leg_b_ = sub_rn(leg_b_, mul_rn(my_bid_, fee));                      /* :46,:48 */          \
-            leg_s_ = sub_rn(leg_s_, mul_rn(my_ask_, fee));                      /* :52,:54 */          \
-        }                                                                                             \
-        double pnl_ = 0.0;                                                      /* :40 */              \
-        pnl_ = p_fb ? add_rn(pnl_, leg_b_) : pnl_;                                                    \
-        pnl_ = p_fs ? add_rn(pnl_, leg_s_) : pnl_;                                                    \
-        const double pen_ = p_ai == 0 ? pen0 : (p_ai == 1 ? pen1 : pen2);       /* :57 */              \
-        total = add_rn(total, sub_rn(pnl_, pen_));                              /* :58, drl_engine.py:54 */ \
-    }
+    // The step loop does the INTEGER half of the env step (offsets, fills, inventory).  Quotes, P&L legs, the
+    // inventory penalty and the reward sum are fp64 in the reference (market_env.py:30-58, drl_engine.py:54): they
+    // run AFTER this kernel from a 64-bit step code per bar (sgmm_account.cu): FP64 and FFMA2 share a half-rate pipe
+    // and the int -> fp64 conversions queue on the XU pipe.
+    // Lane 0 of every individual writes the bar's code (8 bytes; the four stores of a 32-byte sector merge in L2).
+    uint64_t* const crow = a.codes + (live ? ind : 0) * T;
 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int s = (int)(c % RING_STAGES);
@@ -327,7 +306,6 @@ rollout_kernel_h32(const RolloutArgs a)
         const int64_t t0 = c * CHUNK_BARS;
         const int n = (int)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
         const BarSig* sigs = &sm.sig[s][0];
-        const BarPx* pxs = &sm.px[s][0];
 
         // bar 0 of the chunk: signals, thresholds and the inventory-independent part of layer 1
         float4 sg = *reinterpret_cast<const float4*>(&sigs[0]);                     // z1, z2, tha, thb
@@ -354,8 +332,6 @@ rollout_kernel_h32(const RolloutArgs a)
             float A1n[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) A1n[u] = __fmaf_rn(w1y[u], sg.y, __fmaf_rn(w1x[u], sg.x, b1[u]));
-            // ---- deferred fp64 accounting of bar i-1 ---------------------------------------------
-            SGMM_ACCOUNT(pxs[i > 0 ? i - 1 : 0])
             // ---- layer 2: U rows x 32, packed FFMA2, four chains per row -----------------------
             float2 P[U], Q[U];
 #pragma unroll
@@ -409,10 +385,11 @@ rollout_kernel_h32(const RolloutArgs a)
             // ---- quantise + fill decision -------------------------------------------------------
             const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);           // raw*5.0 (drl_engine.py:39)
             const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
-            int ka = __float2int_rn(qa);                                     // np.round(...).astype(int)
-            int kb = __float2int_rn(qb);
+            int ka = 0, kb = 0;
             bool fb, fs;
             if (ADV) {                                                       // drl_engine.py:42-48
+                ka = __float2int_rn(qa);                                     // np.round(...).astype(int)
+                kb = __float2int_rn(qb);
                 const uint32_t e = table_lookup(adv_t0, adv_t1, adv_t2, fsp * 10 + fbp * 5 + inv + 2);
                 ka = max(min(ka, K_CLAMP), -K_CLAMP) + (int)(e & 3u) - 1;    // market_env.py:26-28
                 kb = max(min(kb, K_CLAMP), -K_CLAMP) + (int)(e >> 2) - 1;
@@ -426,22 +403,22 @@ rollout_kernel_h32(const RolloutArgs a)
             }
             inv2 = __fadd_rn(inv2, fb ? (fs ? 0.0f : 0.5f) : (fs ? -0.5f : 0.0f));   // :45,:51 (exact)
             inv += (fb ? 1 : 0) - (fs ? 1 : 0);
-            trades += (fb || fs) ? 1 : 0;                                    // drl_engine.py:60-61
-            // hand the bar to the deferred accounting
-            pk_a = ka; pk_b = kb; p_fb = fb; p_fs = fs; p_ai = inv < 0 ? -inv : inv;
+            // ---- step code: the offset of each side that filled -------------------------------
+            // step code: the offset of each side that filled.  Without the adversary the offsets travel as the fp32
+            // q = raw*5 they are rounded from (the accounting pass rounds them, half-to-even like the oracle): the
+            // float -> int conversion stays off this loop's XU pipe; a NaN pattern marks "no fill"
+            if (l == 0 && live) {
+                if (ADV) __stcs(reinterpret_cast<int2*>(crow + t0 + i), make_int2(fs ? ka : SGMM_CODE_NOFILL, fb ? kb : SGMM_CODE_NOFILL));
+                else __stcs(reinterpret_cast<float2*>(crow + t0 + i), make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F)));
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) A1[u] = A1n[u];
         }
-        // the chunk's last bar must be accounted before its stage is released
-        SGMM_ACCOUNT(pxs[n - 1])
-        p_fb = false; p_fs = false; p_ai = 0;
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
-#undef SGMM_ACCOUNT
-    if (trades == 0) total = sub_rn(total, 50.0);                           // drl_engine.py:64-65
-    if (live && l == 0) { a.fitness[ind] = total; a.trades[ind] = trades; }
 }
+
 
 template <int U, bool ADV, bool FEE>
 static int launch_variant(const RolloutArgs& args, int warps, cudaStream_t st)
@@ -502,12 +479,15 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
     args.mm = mm;
     if (adv) args.adv = *adv; else { PopArgs z = {}; args.adv = z; }
     args.fitness = fitness; args.trades = trades;
-    const bool has_fee = (fee != 0.0);
-    switch (U) {
-        case 1: return launch_u<1>(args, adv != nullptr, has_fee, W, st);
-        case 2: return launch_u<2>(args, adv != nullptr, has_fee, W, st);
-        default: return launch_u<4>(args, adv != nullptr, has_fee, W, st);
+    if (int rc = reserve_codes(b, mm.count, st, &args.codes)) return rc;
+    int rc;
+    switch (U) {                                 // (the fee is the accounting pass's business)
+        case 1: rc = launch_u<1>(args, adv != nullptr, false, W, st); break;
+        case 2: rc = launch_u<2>(args, adv != nullptr, false, W, st); break;
+        default: rc = launch_u<4>(args, adv != nullptr, false, W, st); break;
     }
+    if (rc) return rc;
+    return launch_account(b, args.codes, mm.count, phi, fee, fitness, trades, st, /*float_offsets=*/adv == nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

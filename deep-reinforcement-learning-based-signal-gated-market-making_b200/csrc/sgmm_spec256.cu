@@ -430,10 +430,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
                     const bool fb = (inv < 2) && (kb < kth.y);               // :34,:37
                     const bool fs = (inv > -2) && (ka < kth.x);              // :35,:38
                     const int ninv = inv + (fb ? 1 : 0) - (fs ? 1 : 0);
-                    const int ai = ninv < 0 ? -ninv : ninv;
-                    const int kac = max(min(ka, (1 << 23) - 1), -(1 << 23)), kbc = max(min(kb, (1 << 23) - 1), -(1 << 23));
-                    code = (uint64_t)((uint32_t)kac & 0xFFFFFFu) | ((uint64_t)((uint32_t)kbc & 0xFFFFFFu) << 24) |
-                           ((uint64_t)(fb ? 1u : 0u) << 48) | ((uint64_t)(fs ? 1u : 0u) << 49) | ((uint64_t)ai << 50);
+                    code = (uint64_t)(uint32_t)(fs ? ka : SGMM_CODE_NOFILL) | ((uint64_t)(uint32_t)(fb ? kb : SGMM_CODE_NOFILL) << 32);
                     nxt = (uint32_t)(ninv + 2) | ((fb || fs) ? 8u : 0u);
                     if (a.raw_table) {
                         float* o = a.raw_table + (((int64_t)ind * T + t) * 5 + iv) * 2;
