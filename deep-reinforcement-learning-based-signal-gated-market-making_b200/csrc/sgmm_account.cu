@@ -48,37 +48,38 @@ __global__ void __launch_bounds__(ACC_THREADS) account_kernel(const uint64_t* __
         const double pen0 = mul_rn(phi, 0.0), pen1 = mul_rn(phi, 1.0), pen2 = mul_rn(phi, 2.0);
         const uint64_t none = FLT ? 0xFFFFFFFFFFFFFFFFull : 0x8000000080000000ull;            // no fills beyond T
         uint64_t code_n = (live && lane < T) ? __ldcs(c + lane) : none;                       // window 0
+        // the bars' prices are loaded unconditionally one window ahead (L1/L2-resident: every individual reads the same
+        // bars); loading them only on the lanes that traded put an L2 round trip on every window's critical path
+        double2 ab_n = make_double2(0.0, 0.0); double mid_n = 0.0;
+        if (lane < T) { ab_n = __ldg(reinterpret_cast<const double2*>(&px[lane].ask)); mid_n = __ldg(&px[lane].mid_next); }
         for (int64_t w = 0; w < nwin; ++w) {
             const int64_t t = w * 32 + lane;
             const uint64_t code = code_n;
             const int64_t tn = t + 32;
             code_n = (live && tn < T) ? __ldcs(c + tn) : none;                                   // prefetch the next window
+            const double2 ab = ab_n; const double mid = mid_n;
+            if (tn < T) { ab_n = __ldg(reinterpret_cast<const double2*>(&px[tn].ask)); mid_n = __ldg(&px[tn].mid_next); }
             int ka = (int)(uint32_t)code, kb = (int)(uint32_t)(code >> 32);
             const bool fs = ka != (FLT ? SGMM_CODE_NOFILL_F : SGMM_CODE_NOFILL), fb = kb != (FLT ? SGMM_CODE_NOFILL_F : SGMM_CODE_NOFILL);
-            if (FLT) { ka = __float2int_rn(__int_as_float(ka)); kb = __float2int_rn(__int_as_float(kb)); }   // drl_engine.py:39
-            // inventory after each bar = running sum of the fills (market_env.py:45,51)
-            int d = (fb ? 1 : 0) - (fs ? 1 : 0);
-#pragma unroll
-            for (int m = 1; m < 32; m <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, d, m);
-                if (lane >= m) d += o;
-            }
-            const int ninv = inv + d;
-            inv = __shfl_sync(0xffffffffu, ninv, 31);
+            // inventory after each bar = running sum of the fills (market_env.py:45,51): two ballots instead of a scan
+            const uint32_t mb = __ballot_sync(0xffffffffu, fb), ms = __ballot_sync(0xffffffffu, fs);
+            const uint32_t le = 0xffffffffu >> (31 - lane);                             // lanes 0..lane
+            const int ninv = inv + __popc(mb & le) - __popc(ms & le);
+            inv += __popc(mb) - __popc(ms);
             const bool traded = fb || fs;
-            ntr += __popc(__ballot_sync(0xffffffffu, traded));                          // drl_engine.py:60-61
+            ntr += __popc(mb | ms);                                                     // drl_engine.py:60-61
             const int ai = ninv < 0 ? -ninv : ninv;
             double pnl = 0.0;                                                           // market_env.py:40
             if (traded) {
-                const double2 ab = __ldg(reinterpret_cast<const double2*>(&px[t].ask));
-                const double mid = __ldg(&px[t].mid_next);
                 if (fb) {
+                    if (FLT) kb = __float2int_rn(__int_as_float(kb));                   // drl_engine.py:39 (np.round, half to even)
                     const double my_bid = sub_rn(ab.y, mul_rn((double)kb, tick));       // :31
                     double leg_b = sub_rn(mid, my_bid);
                     if (FEE) leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                // :46,:48
                     pnl = add_rn(pnl, leg_b);
                 }
                 if (fs) {
+                    if (FLT) ka = __float2int_rn(__int_as_float(ka));
                     const double my_ask = add_rn(ab.x, mul_rn((double)ka, tick));       // :30
                     double leg_s = sub_rn(my_ask, mid);
                     if (FEE) leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                // :52,:54
