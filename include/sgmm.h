@@ -48,13 +48,7 @@ extern "C" {
                                     /*         (sgmm_tc32.cu; params.units_per_lane = individuals per */
                                     /*         CTA group, even, 0 = auto)                             */
                                     /*   H=256 hidden and output layer (sgmm_spec256.cu: f16 operands,*/
-                                    /*         f16 layer-2 accumulator, whatever tensor mode is asked;*/
-                                    /*         the rollout kernel records 64-bit step codes in a      */
-                                    /*         grow-only scratch buffer OF THE BUNDLE and a second    */
-                                    /*         kernel does the fp64 accounting: H=256 rollouts on one */
-                                    /*         bundle must be ordered on one stream, and the first    */
-                                    /*         rollout of a given size must not run under a stream    */
-                                    /*         capture (it allocates); offsets saturate at +-2^23)    */
+                                    /*         f16 layer-2 accumulator, whatever tensor mode is asked)*/
                                     /* policy outputs within a stated tolerance of the fp32 oracle;   */
                                     /* the env step given the offsets stays bit-exact                 */
 
@@ -132,7 +126,15 @@ typedef struct {
  * one full episode per individual, fitness[i] = total_reward (with the -50 no-trade penalty,
  * Env/drl_engine.py:64-65), trades[i] = number of steps with at least one fill (:60-61).
  * adv == NULL <=> use_arl False.  adv->count must equal mm->count (MM i meets adversary i).
- * All pointers inside mm / adv and fitness / trades are DEVICE pointers on the bundle's device. */
+ * All pointers inside mm / adv and fitness / trades are DEVICE pointers on the bundle's device.
+ *
+ * Two kernels per call (SGMM_PRECISION_F32, and every H=256 rollout): the rollout kernel does the policy and the integer half of the env step and writes one 8-byte
+ * step code per bar into a grow-only scratch buffer OF THE BUNDLE ([count][T] codes); the accounting kernel then does
+ * the reference's fp64 arithmetic (quotes, P&L, penalty, bar-order reward sum).  Consequences for the caller:
+ *   - rollouts on one bundle must be ordered (one stream, or serialised): they share the scratch;
+ *   - the first rollout of a given size allocates and therefore must not run under a stream capture (run one eagerly,
+ *     then capture; a buffer that has been handed out is never freed before sgmm_bundle_destroy, so captured graphs
+ *     stay valid when a later, larger rollout grows the scratch). */
 int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm,
                             const sgmm_population* adv, const sgmm_rollout_params* params,
                             double* fitness, int32_t* trades, void* stream);
