@@ -31,6 +31,7 @@ namespace sgmm {
 constexpr int RING_STAGES = 4;
 constexpr int CHUNK_BARS = 128;
 constexpr int MAX_WARPS = 16;
+constexpr int REC_STAGES = 2;             // chunks of step records in flight between the compute warps and the accounting warp
 constexpr float ADV_THR = 0.54930615f;   // largest fp32 y with round(tanh(y)) == 0 (tests/golden/tanh_threshold.npz)
 
 // ---------------------------------------------------------------------------------------------
@@ -193,6 +194,10 @@ struct RingSmem {
     BarSig sig[RING_STAGES][CHUNK_BARS];
     float hbuf[MAX_WARPS][128];          // per warp: U individuals x 32 activations, 16-B interleaved
     float rbuf[MAX_WARPS][80];           // per warp: 4 individuals x 8 lanes x (pa,pb), group stride 20 words
+    // step records handed to the accounting warp: one 8-byte code per (bar of the chunk, individual of the CTA)
+    uint64_t rec_full[REC_STAGES];
+    uint64_t rec_empty[REC_STAGES];
+    uint64_t rec[REC_STAGES][CHUNK_BARS][32];
 };
 
 template <int U, bool ADV, bool FEE>
@@ -220,21 +225,78 @@ rollout_kernel_h32(const RolloutArgs a)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], live_warps); }
+#pragma unroll
+        for (int r = 0; r < REC_STAGES; ++r) { mbar_init(&sm.rec_full[r], live_warps); mbar_init(&sm.rec_empty[r], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == nwarps) {
-        // ===== producer warp: one elected lane streams the bar ring, everyone else retires =====
-        if (lane == 0) {
-            for (int64_t c = 0; c < nchunks; ++c) {
-                const int s = (int)(c % RING_STAGES);
-                if (c >= RING_STAGES) mbar_wait(&sm.empty[s], (uint32_t)(((c / RING_STAGES) - 1) & 1));
-                const int64_t t0 = c * CHUNK_BARS;
-                const uint32_t n = (uint32_t)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
-                mbar_arrive_expect_tx(&sm.full[s], n * (uint32_t)sizeof(BarSig));      // (prices are the accounting pass's)
-                tma_bulk_g2s(&sm.sig[s][0], a.sig + t0, n * (uint32_t)sizeof(BarSig), &sm.full[s]);
+        // ===== the CTA's last warp: TMA producer of the bar ring AND the fp64 half of the env step =====
+        // The compute warps do the policy and the INTEGER half of the step and hand one 8-byte record per bar and
+        // individual through shared memory; here lane j accounts individual first + j: quotes, P&L legs, penalty and
+        // the bar-order reward sum in the reference's un-fused fp64 (market_env.py:30-58, drl_engine.py:54).  One
+        // warp instruction per fp64 operation for ALL individuals of the CTA -- in the step loop the same arithmetic
+        // was issued once per compute warp, on the half-rate pipe FFMA2 also runs on (tools/microbench.cu), and cost
+        // 16 % of the loop.
+        const int64_t indj = first + lane;
+        const bool livej = lane < live_warps * NI && indj < a.mm.count;
+        const double tick = a.tick, fee = a.fee;
+        const double pen0 = mul_rn(a.phi, 0.0), pen1 = mul_rn(a.phi, 1.0), pen2 = mul_rn(a.phi, 2.0);   // market_env.py:57
+        double total = 0.0;                                              // drl_engine.py:26
+        int ntr = 0, inv = 0;                                            // market_env.py:17
+        int64_t next_load = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            // keep the bar ring RING_STAGES chunks ahead of the chunk being accounted
+            const int64_t lim = c + RING_STAGES < nchunks ? c + RING_STAGES : nchunks;
+            for (; next_load < lim; ++next_load) {
+                if (lane == 0) {
+                    const int s = (int)(next_load % RING_STAGES);
+                    if (next_load >= RING_STAGES) mbar_wait(&sm.empty[s], (uint32_t)(((next_load / RING_STAGES) - 1) & 1));
+                    const int64_t tl = next_load * CHUNK_BARS;
+                    const uint32_t nb = (uint32_t)(T - tl < CHUNK_BARS ? T - tl : CHUNK_BARS);
+                    mbar_arrive_expect_tx(&sm.full[s], nb * (uint32_t)sizeof(BarSig));
+                    tma_bulk_g2s(&sm.sig[s][0], a.sig + tl, nb * (uint32_t)sizeof(BarSig), &sm.full[s]);
+                }
             }
+            __syncwarp();
+            const int r = (int)(c % REC_STAGES);
+            mbar_wait(&sm.rec_full[r], (uint32_t)((c / REC_STAGES) & 1));
+            const int64_t t0 = c * CHUNK_BARS;
+            const int n = (int)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) {
+                const uint64_t code = sm.rec[r][i][lane];
+                int ka = (int)(uint32_t)code, kb = (int)(uint32_t)(code >> 32);
+                const bool fs = ka != (ADV ? SGMM_CODE_NOFILL : SGMM_CODE_NOFILL_F), fb = kb != (ADV ? SGMM_CODE_NOFILL : SGMM_CODE_NOFILL_F);
+                inv += (fb ? 1 : 0) - (fs ? 1 : 0);                      // market_env.py:45,51
+                const int ai = inv < 0 ? -inv : inv;
+                const bool traded = fb || fs;
+                ntr += traded ? 1 : 0;                                   // drl_engine.py:60-61
+                double pnl = 0.0;                                        // market_env.py:40
+                if (__any_sync(0xffffffffu, traded)) {
+                    const double2 ab = __ldg(reinterpret_cast<const double2*>(&a.px[t0 + i].ask));
+                    const double mid = __ldg(&a.px[t0 + i].mid_next);
+                    if (!ADV) { ka = __float2int_rn(__int_as_float(ka)); kb = __float2int_rn(__int_as_float(kb)); }   // drl_engine.py:39
+                    const double my_ask = add_rn(ab.x, mul_rn((double)ka, tick));       // market_env.py:30
+                    const double my_bid = sub_rn(ab.y, mul_rn((double)kb, tick));       // :31
+                    double leg_b = sub_rn(mid, my_bid), leg_s = sub_rn(my_ask, mid);
+                    if (FEE) {
+                        leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                     // :46,:48
+                        leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                     // :52,:54
+                    }
+                    pnl = fb ? add_rn(pnl, leg_b) : pnl;
+                    pnl = fs ? add_rn(pnl, leg_s) : pnl;
+                }
+                const double pen = ai == 0 ? pen0 : (ai == 1 ? pen1 : pen2);            // :57
+                total = add_rn(total, sub_rn(pnl, pen));                                // :58, drl_engine.py:54
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.rec_empty[r]);
+        }
+        if (livej) {
+            if (ntr == 0) total = sub_rn(total, 50.0);                                  // drl_engine.py:64-65
+            a.fitness[indj] = total; a.trades[indj] = ntr;
         }
         return;
     }
@@ -292,17 +354,18 @@ rollout_kernel_h32(const RolloutArgs a)
     int inv = 0, fbp = 0, fsp = 0;
     float inv2 = 0.0f;                                               // inventory / 2.0 (drl_engine.py:35), exact
 
-    // The step loop does the INTEGER half of the env step (offsets, fills, inventory).  Quotes, P&L legs, the
-    // inventory penalty and the reward sum are fp64 in the reference (market_env.py:30-58, drl_engine.py:54): they
-    // run AFTER this kernel from a 64-bit step code per bar (sgmm_account.cu): FP64 and FFMA2 share a half-rate pipe
-    // and the int -> fp64 conversions queue on the XU pipe.
-    // Lane 0 of every individual writes the bar's code (8 bytes; the four stores of a 32-byte sector merge in L2).
-    uint64_t* const crow = a.codes + (live ? ind : 0) * T;
+    // The step loop does the INTEGER half of the env step (offsets, fills, inventory) and hands one 8-byte record per
+    // bar to the accounting warp (above): the offset of each side that filled, or a no-fill marker.  Without the
+    // adversary the offsets travel as the fp32 q = raw*5 they are rounded from (no conversion in this loop).
+    const int slotj = warp * NI + g;                                 // this individual's lane in the accounting warp
 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int s = (int)(c % RING_STAGES);
         mbar_wait(&sm.full[s], (uint32_t)((c / RING_STAGES) & 1));
+        const int r = (int)(c % REC_STAGES);
+        if (c >= REC_STAGES) mbar_wait(&sm.rec_empty[r], (uint32_t)(((c / REC_STAGES) - 1) & 1));   // records of chunk c - 2 accounted
         __syncwarp();
+        uint64_t* const recs = &sm.rec[r][0][slotj];
         const int64_t t0 = c * CHUNK_BARS;
         const int n = (int)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
         const BarSig* sigs = &sm.sig[s][0];
@@ -404,18 +467,15 @@ rollout_kernel_h32(const RolloutArgs a)
             inv2 = __fadd_rn(inv2, fb ? (fs ? 0.0f : 0.5f) : (fs ? -0.5f : 0.0f));   // :45,:51 (exact)
             inv += (fb ? 1 : 0) - (fs ? 1 : 0);
             // ---- step code: the offset of each side that filled -------------------------------
-            // step code: the offset of each side that filled.  Without the adversary the offsets travel as the fp32
-            // q = raw*5 they are rounded from (the accounting pass rounds them, half-to-even like the oracle): the
-            // float -> int conversion stays off this loop's XU pipe; a NaN pattern marks "no fill"
-            if (l == 0 && live) {
-                if (ADV) __stcs(reinterpret_cast<int2*>(crow + t0 + i), make_int2(fs ? ka : SGMM_CODE_NOFILL, fb ? kb : SGMM_CODE_NOFILL));
-                else __stcs(reinterpret_cast<float2*>(crow + t0 + i), make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F)));
+            if (l == 0) {
+                if (ADV) *reinterpret_cast<int2*>(recs + i * 32) = make_int2(fs ? ka : SGMM_CODE_NOFILL, fb ? kb : SGMM_CODE_NOFILL);
+                else *reinterpret_cast<float2*>(recs + i * 32) = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) A1[u] = A1n[u];
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);
+        if (lane == 0) { mbar_arrive(&sm.empty[s]); mbar_arrive(&sm.rec_full[r]); }
     }
 }
 
@@ -479,15 +539,13 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
     args.mm = mm;
     if (adv) args.adv = *adv; else { PopArgs z = {}; args.adv = z; }
     args.fitness = fitness; args.trades = trades;
-    if (int rc = reserve_codes(b, mm.count, st, &args.codes)) return rc;
-    int rc;
-    switch (U) {                                 // (the fee is the accounting pass's business)
-        case 1: rc = launch_u<1>(args, adv != nullptr, false, W, st); break;
-        case 2: rc = launch_u<2>(args, adv != nullptr, false, W, st); break;
-        default: rc = launch_u<4>(args, adv != nullptr, false, W, st); break;
+    args.codes = nullptr;
+    const bool has_fee = (fee != 0.0);
+    switch (U) {
+        case 1: return launch_u<1>(args, adv != nullptr, has_fee, W, st);
+        case 2: return launch_u<2>(args, adv != nullptr, has_fee, W, st);
+        default: return launch_u<4>(args, adv != nullptr, has_fee, W, st);
     }
-    if (rc) return rc;
-    return launch_account(b, args.codes, mm.count, phi, fee, fitness, trades, st, /*float_offsets=*/adv == nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
