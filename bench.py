@@ -405,26 +405,23 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": P_PER_GPU * G * 4 * n_gpus,
                     "d2h_bytes_per_step": P_PER_GPU * 12 * n_gpus, "ms_per_step": 1e3 * e2e_s / K,
                     "entry": "sgmm_rollout_population_host (pinned host genomes in, fitness/trades out; bundle resident)"},
-            "gpu_launches": (2 + len(TC_MODES)) * K,    # per timed step: rollout_kernel_h32 + account_kernel; plus K tensor-core rollouts per mode
+            "gpu_launches": (1 + len(TC_MODES)) * K,    # K exact-kernel + K tensor-core rollouts per mode in the device-timed regions
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak if fp32_peak else None,
-                         "traffic": 123973888,
-                         "kernel": "rollout_kernel_h32<4,false,false> (94 % of the step) + account_kernel<false,true>",
+                         "traffic": 20922880,
+                         "kernel": "rollout_kernel_h32<4,false,false>",
                          "algorithmic_flop_per_env_step": FLOP_PER_STEP,
                          "peak_source": "FFMA/FFMA2 peak measured live on this device by sgmm_measure_fp32_peak "
                                         "(MEASURED_PEAKS.json has no fp32 figure; theoretical 74.4 TFLOP/s at 1965 MHz)",
                          "note": "compute-bound on the FP32 CUDA-core pipe (SURVEY.md 8d); bound is neither hbm nor tensor. "
-                                 "achieved uses the whole step (both kernels). traffic = dram__bytes_read+write of one "
-                                 "rollout_kernel_h32 launch from profiles/r1_rollout_codes_ncu_full.txt (P=4096, T=4800: 20.8 MB "
-                                 "read = the genomes once, bars stay in L2; 103 MB written = the 8-byte step codes that had left "
-                                 "L2 by the end of the kernel, at most 8 B per env-step; the accounting kernel reads them back: "
-                                 "1.5 % of HBM bandwidth, the price of keeping FP64 out of the FFMA2 loop)",
+                                 "traffic = dram__bytes_read+write of one launch from profiles/r1_rollout_accwarp_ncu_full.txt "
+                                 "(P=4096: 20.9 MB read, i.e. the genomes once; bars stay in L2; nothing written but the results)",
                          "hbm": {"achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
                                  "peak_source": hbm_src}},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "traffic": 123973888,
+                             "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "traffic": 20922880,
                              "note": "reported for completeness: the bar/genome stream is <0.1% of HBM peak by construction"},
             "roofline_tensor_h256": (None if not h256 or "error" in h256 else
                                      {"bound": "tensor", "achieved": h256["algorithmic_tflops"],

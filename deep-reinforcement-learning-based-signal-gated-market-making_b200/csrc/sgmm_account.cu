@@ -8,11 +8,10 @@
 // a 64-bit code; this kernel turns the codes into rewards and sums them in the reference's order:
 //     code = (fill_sell ? off_a : SGMM_CODE_NOFILL) | (fill_buy ? off_b : SGMM_CODE_NOFILL) << 32      (two int32)
 // (an offset is only needed on a side that filled; the inventory is re-derived here as the running sum of the fills).
-// The exact H=32 kernel uses the same split (FFMA2 and FP64 instructions share a half-rate pipe, and the int -> fp64
-// conversions sit on the XU pipe): at P = 4096 x 14 400 bars its step loop went from 5.25 ms with the fp64 accounting
-// inside to 4.79 ms writing codes (4.42 with neither), and this kernel takes 0.32 ms.
-// One warp per individual: 32 bars' rewards in parallel (un-fused fp64 in the reference's op order), then the
-// running sum bar by bar through shuffles (the only serial part: one DADD per bar).
+// The exact H=32 kernel (sgmm_rollout.cu) uses the same split INSIDE one kernel: its compute warps hand the step
+// records through shared memory to the CTA's producer warp, which accounts all individuals of the CTA (lane =
+// individual).  Here the codes go through global memory because the H=256 kernel works on one individual per CTA
+// and its fp64 would run next to the MMAs whichever warp issued it.
 #include "sgmm_internal.h"
 #include "sgmm_step_core.h"
 

@@ -18,9 +18,11 @@
 //     release a stage through an "empty" mbarrier and a dedicated producer warp refills it;
 //   * the env step is branch-free: fills are integer compares against per-bar thresholds derived
 //     once per bundle with the reference's exact fp64 expression, inventory is an integer;
-//   * quotes / P&L / penalty / reward sum -- un-fused fp64 in the reference's order -- are NOT in this
-//     kernel: it records a 64-bit step code per bar and sgmm_account.cu does the fp64 half afterwards
-//     (measured at P = 4096 x 14 400 bars: 5.25 ms with the accounting in the loop, 4.79 + 0.32 ms split).
+//   * quotes / P&L / penalty / reward sum -- un-fused fp64 in the reference's order -- are NOT in the
+//     step loop: the compute warps hand one 8-byte record per bar through shared memory to the CTA's
+//     producer warp, whose lane j accounts individual j of the CTA (one fp64 warp instruction for all 28
+//     individuals instead of one per compute warp on the half-rate pipe FFMA2 shares).  Measured at
+//     P = 4096 x 14 400 bars: 5.25 ms with the accounting in the loop, 4.55 ms this way.
 #include <cstdio>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"

@@ -128,13 +128,14 @@ typedef struct {
  * adv == NULL <=> use_arl False.  adv->count must equal mm->count (MM i meets adversary i).
  * All pointers inside mm / adv and fitness / trades are DEVICE pointers on the bundle's device.
  *
- * Two kernels per call (SGMM_PRECISION_F32, and every H=256 rollout): the rollout kernel does the policy and the integer half of the env step and writes one 8-byte
- * step code per bar into a grow-only scratch buffer OF THE BUNDLE ([count][T] codes); the accounting kernel then does
- * the reference's fp64 arithmetic (quotes, P&L, penalty, bar-order reward sum).  Consequences for the caller:
+ * H = 256 rollouts are two kernels: the tensor-core rollout kernel does the policy and the integer half of the env step
+ * and writes one 8-byte step code per bar into a grow-only scratch buffer OF THE BUNDLE ([count][T] codes); an
+ * accounting kernel then does the reference's fp64 arithmetic (an FP64 instruction issued while tcgen05.mma executes
+ * waits ~80x longer).  Consequences for the caller of H = 256 rollouts:
  *   - rollouts on one bundle must be ordered (one stream, or serialised): they share the scratch;
  *   - the first rollout of a given size allocates and therefore must not run under a stream capture (run one eagerly,
- *     then capture; a buffer that has been handed out is never freed before sgmm_bundle_destroy, so captured graphs
- *     stay valid when a later, larger rollout grows the scratch). */
+ *     then capture; a buffer that has been handed out is never freed before sgmm_bundle_destroy).
+ * H = 32 rollouts (every precision) are one kernel with no scratch. */
 int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm,
                             const sgmm_population* adv, const sgmm_rollout_params* params,
                             double* fitness, int32_t* trades, void* stream);
