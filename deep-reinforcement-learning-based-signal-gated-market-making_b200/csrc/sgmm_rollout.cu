@@ -194,6 +194,7 @@ struct RingSmem {
     uint64_t full[RING_STAGES];
     uint64_t empty[RING_STAGES];
     BarSig sig[RING_STAGES][CHUNK_BARS];
+    BarPx px[RING_STAGES][CHUNK_BARS];   // prices: read by the accounting warp only
     float hbuf[MAX_WARPS][128];          // per warp: U individuals x 32 activations, 16-B interleaved
     float rbuf[MAX_WARPS][80];           // per warp: 4 individuals x 8 lanes x (pa,pb), group stride 20 words
     // step records handed to the accounting warp: one 8-byte code per (bar of the chunk, individual of the CTA)
@@ -257,8 +258,9 @@ rollout_kernel_h32(const RolloutArgs a)
                     if (next_load >= RING_STAGES) mbar_wait(&sm.empty[s], (uint32_t)(((next_load / RING_STAGES) - 1) & 1));
                     const int64_t tl = next_load * CHUNK_BARS;
                     const uint32_t nb = (uint32_t)(T - tl < CHUNK_BARS ? T - tl : CHUNK_BARS);
-                    mbar_arrive_expect_tx(&sm.full[s], nb * (uint32_t)sizeof(BarSig));
+                    mbar_arrive_expect_tx(&sm.full[s], nb * (uint32_t)(sizeof(BarSig) + sizeof(BarPx)));
                     tma_bulk_g2s(&sm.sig[s][0], a.sig + tl, nb * (uint32_t)sizeof(BarSig), &sm.full[s]);
+                    tma_bulk_g2s(&sm.px[s][0], a.px + tl, nb * (uint32_t)sizeof(BarPx), &sm.full[s]);
                 }
             }
             __syncwarp();
@@ -266,6 +268,9 @@ rollout_kernel_h32(const RolloutArgs a)
             mbar_wait(&sm.rec_full[r], (uint32_t)((c / REC_STAGES) & 1));
             const int64_t t0 = c * CHUNK_BARS;
             const int n = (int)(T - t0 < CHUNK_BARS ? T - t0 : CHUNK_BARS);
+            // the chunk's prices sit in its ring stage (complete: the compute warps waited for the same barrier, and
+            // the stage is refilled by this warp only after this loop)
+            const BarPx* pxs = &sm.px[c % RING_STAGES][0];
 #pragma unroll 4
             for (int i = 0; i < n; ++i) {
                 const uint64_t code = sm.rec[r][i][lane];
@@ -277,8 +282,8 @@ rollout_kernel_h32(const RolloutArgs a)
                 ntr += traded ? 1 : 0;                                   // drl_engine.py:60-61
                 double pnl = 0.0;                                        // market_env.py:40
                 if (__any_sync(0xffffffffu, traded)) {
-                    const double2 ab = __ldg(reinterpret_cast<const double2*>(&a.px[t0 + i].ask));
-                    const double mid = __ldg(&a.px[t0 + i].mid_next);
+                    const double2 ab = *reinterpret_cast<const double2*>(&pxs[i].ask);
+                    const double mid = pxs[i].mid_next;
                     if (!ADV) { ka = __float2int_rn(__int_as_float(ka)); kb = __float2int_rn(__int_as_float(kb)); }   // drl_engine.py:39
                     const double my_ask = add_rn(ab.x, mul_rn((double)ka, tick));       // market_env.py:30
                     const double my_bid = sub_rn(ab.y, mul_rn((double)kb, tick));       // :31
