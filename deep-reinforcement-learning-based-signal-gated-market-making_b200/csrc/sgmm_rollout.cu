@@ -519,9 +519,6 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
 {
     if (hidden != 32) { set_error("hidden=%d: the SGMM-F32 rollout kernel is built for H=32", hidden); return SGMM_ERR_UNSUPPORTED; }
     if (mm.count == 0) return SGMM_OK;
-    int U = units_per_lane;
-    if (U == 0) U = 4;
-    if (U != 1 && U != 2 && U != 4) { set_error("units_per_lane must be 0, 1, 2 or 4"); return SGMM_ERR_INVALID; }
     int dev = b->device;
     if (dev >= 0 && dev < 64 && g_sm_count[dev] == 0) {
         int n = 0;
@@ -529,6 +526,12 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
         g_sm_count[dev] = n;
     }
     const int sms = (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) ? g_sm_count[dev] : 148;
+    int U = units_per_lane;
+    // auto: a whole warp per individual while that still leaves at most one compute warp per scheduler (the step of a
+    // lone warp is latency-bound and shortest with 32 lanes per individual: P = 50 x 14 400 bars 2.49 instead of 2.87 ms,
+    // P = 512 2.69 / 2.87), four individuals per warp beyond (P = 1024: 2.90 / 3.10 ms, P = 4096: 4.5 / 8.2)
+    if (U == 0) U = (mm.count <= 4 * (int64_t)sms) ? 1 : 4;
+    if (U != 1 && U != 2 && U != 4) { set_error("units_per_lane must be 0, 1, 2 or 4"); return SGMM_ERR_INVALID; }
     int W = warps_per_cta;
     if (W == 0) {
         // one CTA per SM per wave; spread the population evenly over the SMs of each wave
