@@ -21,8 +21,8 @@
 //   * quotes / P&L / penalty / reward sum -- un-fused fp64 in the reference's order -- are NOT in the
 //     step loop: the compute warps hand one 8-byte record per bar through shared memory to the CTA's
 //     producer warp, whose lane j accounts individual j of the CTA (one fp64 warp instruction for all 28
-//     individuals instead of one per compute warp on the half-rate pipe FFMA2 shares).  Measured at
-//     P = 4096 x 14 400 bars: 5.25 ms with the accounting in the loop, 4.55 ms this way.
+//     individuals instead of one per compute warp, and no int -> fp64 conversions or fp64 registers in the
+//     step loop).  Measured at P = 4096 x 14 400 bars: 5.25 ms with the accounting in the loop, 4.53 ms this way.
 #include <cstdio>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
@@ -240,8 +240,8 @@ rollout_kernel_h32(const RolloutArgs a)
         // individual through shared memory; here lane j accounts individual first + j: quotes, P&L legs, penalty and
         // the bar-order reward sum in the reference's un-fused fp64 (market_env.py:30-58, drl_engine.py:54).  One
         // warp instruction per fp64 operation for ALL individuals of the CTA -- in the step loop the same arithmetic
-        // was issued once per compute warp, on the half-rate pipe FFMA2 also runs on (tools/microbench.cu), and cost
-        // 16 % of the loop.
+        // was issued once per compute warp (22 of 217 instructions, two of them conversions on the XU pipe, plus the
+        // fp64 live ranges in a 254-register kernel) and cost 16 % of the loop.
         const int64_t indj = first + lane;
         const bool livej = lane < live_warps * NI && indj < a.mm.count;
         const double tick = a.tick, fee = a.fee;

@@ -32,8 +32,8 @@ __global__ void lat_kernel(float* out, long long* cyc, float a, double da, int i
 template <int OP>
 __global__ void tput_kernel(float* out, float a, double da)
 {
-    float x[8]; float2 x2[8]; double d[8];
-    for (int j = 0; j < 8; ++j) { x[j] = a + j + threadIdx.x; x2[j] = make_float2(x[j], x[j]); d[j] = da + j; }
+    float x[8]; float2 x2[8]; double d[8]; float2 w2r[8]; float2 h2r = make_float2(a * 0.5f, a * 0.25f);
+    for (int j = 0; j < 8; ++j) { x[j] = a + j + threadIdx.x; x2[j] = make_float2(x[j], x[j]); d[j] = da + j; w2r[j] = make_float2(1.0f + 1e-7f * (j + threadIdx.x), 1.0f - 1e-7f * j); }
     for (int i = 0; i < N; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -42,6 +42,14 @@ __global__ void tput_kernel(float* out, float a, double da)
             if (OP == 2) d[j] = __dadd_rn(d[j], 1e-7);
             if (OP == 3) d[j] = __dmul_rn(d[j], 1.0000001);
             if (OP == 9) { x2[j] = __ffma2_rn(x2[j], make_float2(x[j], x[(j + 1) & 7]), x2[(j + 3) & 7]); }
+            // mixes: do FFMA and FFMA2 (or FFMA2 and DADD) run on separate pipes?  OP 10: one FFMA2 + one FFMA; OP 11: one FFMA2 + two FFMA;
+            // OP 12: one FFMA2 + one DADD (counted in lane-FMAs resp. instructions by the caller)
+            if (OP == 10) { x2[j] = __ffma2_rn(x2[j], make_float2(1.0000001f, 0.9999999f), make_float2(1e-7f, 1e-7f)); x[j] = __fmaf_rn(x[j], 1.0000001f, 1e-7f); }
+            if (OP == 11) { x2[j] = __ffma2_rn(x2[j], make_float2(1.0000001f, 0.9999999f), make_float2(1e-7f, 1e-7f)); x[j] = __fmaf_rn(x[j], 1.0000001f, 1e-7f); d[j] = __hiloint2double(__float_as_int(__fmaf_rn(__int_as_float(__double2hiint(d[j])), 1.0000001f, 1e-7f)), __double2loint(d[j])); }
+            // the hidden-layer pattern of sgmm_rollout.cu: 8 independent accumulators, weights and activations in registers
+            if (OP == 13) { x2[j] = __ffma2_rn(w2r[j], h2r, x2[j]); }
+            if (OP == 14) { x[j] = __fmaf_rn(w2r[j].x, h2r.x, x[j]); }
+            if (OP == 12) { x2[j] = __ffma2_rn(x2[j], make_float2(1.0000001f, 0.9999999f), make_float2(1e-7f, 1e-7f)); d[j] = __dadd_rn(d[j], 1e-7); }
         }
     }
     float s = 0; for (int j = 0; j < 8; ++j) s += x[j] + x2[j].x + x2[j].y + (float)d[j];
@@ -76,6 +84,8 @@ int main()
     run_lat<6>("SHFL.BFLY+FADD", out, cyc); run_lat<7>("LDS.128 chase", out, cyc); run_lat<8>("STS+sync+LDS+sync+FADD", out, cyc);
     run_tput<0>("FFMA", out, 1); run_tput<1>("FFMA2", out, 2); run_tput<2>("DADD", out, 1); run_tput<3>("DMUL", out, 1);
     run_tput<9>("FFMA2 (reg operands)", out, 2);
+    run_tput<10>("1 FFMA2 + 1 FFMA (3 FMA/iter)", out, 3); run_tput<11>("1 FFMA2 + 2 FFMA (4 FMA/iter)", out, 4); run_tput<12>("1 FFMA2 + 1 DADD (2 instr)", out, 2);
+    run_tput<13>("FFMA2 acc += w(reg) * h(reg)", out, 2); run_tput<14>("FFMA  acc += w(reg) * h(reg)", out, 1);
     printf("cuda error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
