@@ -62,7 +62,7 @@ class StepInfo(C.Structure):
 
 class GaConfig(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("use_arl", C.c_int32), ("pop_size", C.c_int64),
-                ("shard_first", C.c_int64), ("shard_count", C.c_int64),
+                ("shard_first", C.c_int64), ("shard_count", C.c_int64), ("shard_stride", C.c_int64),
                 ("sigma", C.c_float), ("patience", C.c_int32),
                 ("phi", C.c_double), ("fee_rate", C.c_double), ("seed", C.c_uint64),
                 ("max_generations", C.c_int32), ("precision", C.c_int32)]
@@ -78,6 +78,7 @@ class GaStatus(C.Structure):
 SIGNATURES = {
     "sgmm_version": (C.c_int, []),
     "sgmm_last_error": (C.c_char_p, []),
+    "sgmm_abi_sizeof": (C.c_int, [C.c_int]),
     "sgmm_device_count": (C.c_int, []),
     "sgmm_device_info": (C.c_int, [C.c_int, i32p, i32p, i32p, C.POINTER(C.c_uint64)]),
     "sgmm_bundle_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -91,6 +92,9 @@ SIGNATURES = {
                                           C.POINTER(RolloutParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgmm_rollout_population_host": (C.c_int, [C.c_void_p, C.POINTER(Population), C.POINTER(Population),
                                                C.POINTER(RolloutParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgmm_rollout_population_host_async": (C.c_int, [C.c_void_p, C.POINTER(Population), C.POINTER(Population),
+                                                     C.POINTER(RolloutParams), C.c_void_p, C.c_void_p, i32p]),
+    "sgmm_rollout_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "sgmm_rollout_spec256_audit": (C.c_int, [C.c_void_p, C.POINTER(Population), C.POINTER(RolloutParams), C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgmm_rollout_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
@@ -101,11 +105,13 @@ SIGNATURES = {
     "sgmm_env_init": (C.c_int, [C.POINTER(EnvState), C.c_double, C.c_double, C.c_double]),
     "sgmm_env_step_host": (C.c_int, [C.POINTER(EnvState), i64p, i64p, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.POINTER(StepInfo)]),
+    "sgmm_env_step_host_real": (C.c_int, [C.POINTER(EnvState), f64p, i64p, C.c_double, C.c_double, C.c_double,
+                                          C.c_double, C.c_double, C.POINTER(StepInfo)]),
     "sgmm_ga_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(GaConfig), C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_void_p]),
     "sgmm_ga_destroy": (C.c_int, [C.c_void_p]),
-    "sgmm_ga_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "sgmm_ga_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                  i64p, i32p, i32p]),
     "sgmm_ga_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgmm_ga_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgmm_ga_generation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -147,6 +153,10 @@ def lib():
                 raise SgmmLibraryError(f"{LIB_PATH} does not export {name}") from e
             fn.restype = res
             fn.argtypes = args
+        for which, struct in enumerate((Population, RolloutParams, Trace, EnvState, StepInfo, GaConfig, GaStatus)):
+            if L.sgmm_abi_sizeof(which) != C.sizeof(struct):
+                raise SgmmLibraryError(f"{LIB_PATH}: sizeof({struct.__name__}) is {L.sgmm_abi_sizeof(which)} in the library, "
+                                       f"{C.sizeof(struct)} in the ctypes mirror -- rebuild the library (stale .so?)")
         _lib = L
     return _lib
 

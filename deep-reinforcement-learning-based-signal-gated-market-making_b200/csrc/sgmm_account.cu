@@ -138,22 +138,43 @@ int reserve_codes(const sgmm_bundle* cb, int64_t count, cudaStream_t st, uint64_
     sgmm_bundle* b = const_cast<sgmm_bundle*>(cb);
     std::lock_guard<std::mutex> lock(b->codes_mutex);
     const size_t want = (size_t)count * (size_t)b->T;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st) cudaStreamIsCapturing(st, &cap);
+    // another stream used the buffer last: order this rollout after its accounting kernel (a capture cannot wait on an
+    // event recorded outside it -- captured rollouts of one bundle must stay on one stream, as the header says)
+    if (b->codes_busy && b->codes_stream != st && cap == cudaStreamCaptureStatusNone && b->codes_done)
+        if (int rc = check_cuda(cudaStreamWaitEvent(st, b->codes_done, 0), "cudaStreamWaitEvent(code buffer)")) return rc;
+    if (cap != cudaStreamCaptureStatusNone) b->codes_captured = true;
     if (b->codes_cap < want) {
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (st) cudaStreamIsCapturing(st, &cap);
         if (cap != cudaStreamCaptureStatusNone) {
             set_error("the code buffer of the bundle holds %zu codes, this rollout needs %zu: run one rollout of this size outside "
                       "the stream capture first", b->codes_cap, want);
             return SGMM_ERR_INVALID;
         }
-        // the old buffer stays alive until the bundle is destroyed: a captured CUDA graph may hold its address
-        if (b->codes) b->codes_retired.push_back(b->codes);
+        // a captured CUDA graph may hold the old buffer's address: once any capture has used this bundle's code buffer the
+        // outgrown buffers stay alive until the bundle is destroyed; otherwise cudaFree (which synchronises the device,
+        // so every enqueued user is done) returns the memory now -- no unbounded growth when population sizes vary
+        if (b->codes) { if (b->codes_captured) b->codes_retired.push_back(b->codes); else cudaFree(b->codes); }
         b->codes = nullptr; b->codes_cap = 0;
         const size_t grow = want + want / 4;
         if (int rc = check_cuda(cudaMalloc(&b->codes, grow * sizeof(uint64_t)), "cudaMalloc(code buffer)")) return rc;
         b->codes_cap = grow;
     }
     *out = b->codes;
+    return SGMM_OK;
+}
+
+int release_codes(const sgmm_bundle* cb, cudaStream_t st)
+{
+    sgmm_bundle* b = const_cast<sgmm_bundle*>(cb);
+    std::lock_guard<std::mutex> lock(b->codes_mutex);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st) cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return SGMM_OK;
+    if (!b->codes_done)
+        if (int rc = check_cuda(cudaEventCreateWithFlags(&b->codes_done, cudaEventDisableTiming), "cudaEventCreate(code buffer)")) return rc;
+    if (int rc = check_cuda(cudaEventRecord(b->codes_done, st), "cudaEventRecord(code buffer)")) return rc;
+    b->codes_stream = st; b->codes_busy = true;
     return SGMM_OK;
 }
 

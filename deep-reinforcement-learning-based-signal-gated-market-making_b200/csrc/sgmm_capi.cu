@@ -31,13 +31,13 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-static int ensure_workspace(sgmm_bundle* b, size_t bytes)
+static int ensure_workspace(sgmm_bundle* b, int slot, size_t bytes)
 {
-    if (b->ws_bytes >= bytes) return SGMM_OK;
-    if (b->ws) { cudaFree(b->ws); b->ws = nullptr; b->ws_bytes = 0; }
+    if (b->ws_bytes[slot] >= bytes) return SGMM_OK;
+    if (b->ws[slot]) { cudaFree(b->ws[slot]); b->ws[slot] = nullptr; b->ws_bytes[slot] = 0; }   // cudaFree synchronises: no user left
     size_t want = bytes + bytes / 4 + 4096;
-    if (int rc = check_cuda(cudaMalloc(&b->ws, want), "cudaMalloc(workspace)")) return rc;
-    b->ws_bytes = want;
+    if (int rc = check_cuda(cudaMalloc(&b->ws[slot], want), "cudaMalloc(workspace)")) return rc;
+    b->ws_bytes[slot] = want;
     return SGMM_OK;
 }
 
@@ -60,6 +60,20 @@ extern "C" {
 
 int sgmm_version(void) { return SGMM_VERSION; }
 const char* sgmm_last_error(void) { return g_err; }
+
+int sgmm_abi_sizeof(int which)
+{
+    switch (which) {
+        case 0: return (int)sizeof(sgmm_population);
+        case 1: return (int)sizeof(sgmm_rollout_params);
+        case 2: return (int)sizeof(sgmm_trace);
+        case 3: return (int)sizeof(sgmm_env_state);
+        case 4: return (int)sizeof(sgmm_step_info);
+        case 5: return (int)sizeof(sgmm_ga_config);
+        case 6: return (int)sizeof(sgmm_ga_status);
+        default: return SGMM_ERR_INVALID;
+    }
+}
 
 int sgmm_device_count(void)
 {
@@ -167,8 +181,10 @@ int sgmm_bundle_destroy(sgmm_bundle* b)
     if (!b) return SGMM_OK;
     {
         DeviceGuard guard(b->device);
-        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->a1); cudaFree(b->ws); cudaFree(b->codes);
+        cudaFree(b->sig); cudaFree(b->px); cudaFree(b->bmax); cudaFree(b->smin); cudaFree(b->a1); cudaFree(b->codes);
+        for (int k = 0; k < SGMM_HOST_SLOTS; ++k) { if (b->slot_stream[k]) { cudaStreamSynchronize(b->slot_stream[k]); cudaStreamDestroy(b->slot_stream[k]); } cudaFree(b->ws[k]); }
         for (uint64_t* p : b->codes_retired) cudaFree(p);
+        if (b->codes_done) cudaEventDestroy(b->codes_done);
     }
     delete b;
     return SGMM_OK;
@@ -202,7 +218,7 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
     if (mm->hidden == 256)
         return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, nullptr, nullptr, (cudaStream_t)stream);
     if (params->precision != SGMM_PRECISION_F32)
-        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, nullptr, nullptr,
+        return launch_tc32(bundle, pm, adv ? &pa : nullptr, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, nullptr, nullptr,
                            (cudaStream_t)stream, tc32_mode_of(params->precision));
     return launch_rollout(bundle, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                           params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
@@ -217,27 +233,23 @@ int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population*
     if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
     DeviceGuard guard(bundle->device);
     if (mm->hidden == 32)
-        return launch_tc32(bundle, pm, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace,
+        return launch_tc32(bundle, pm, nullptr, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace,
                            (cudaStream_t)stream, tc32_mode_of(params->precision));
     return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
 }
 
-int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
-                                 const sgmm_rollout_params* params, double* fitness, int32_t* trades, void* stream)
+// One host-buffer rollout enqueued on `st` using workspace slot `slot` of the bundle: H2D genomes, kernel(s), D2H results.
+// No synchronisation; the caller holds the slot's mutex-free ownership (the public entries serialise per slot).
+static int enqueue_host_rollout(sgmm_bundle* b, int slot, const sgmm_population* mm, const sgmm_population* adv,
+                                const sgmm_rollout_params* params, double* fitness, int32_t* trades, cudaStream_t st)
 {
-    if (int rc = check_rollout_args(bundle, mm, adv, params, fitness, trades)) return rc;
-    if (mm->count == 0) return SGMM_OK;
-    sgmm_bundle* b = const_cast<sgmm_bundle*>(bundle);
-    std::lock_guard<std::mutex> lock(b->ws_mutex);
-    DeviceGuard guard(b->device);
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t P = mm->count, G = genome_len(mm->hidden), GA = 1250;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t mm_bytes = align((size_t)(mm->genomes ? P * G : G) * sizeof(float));
     const size_t adv_bytes = adv ? align((size_t)(adv->genomes ? P * GA : GA) * sizeof(float)) : 0;
     const size_t fit_bytes = align((size_t)P * sizeof(double)), trd_bytes = align((size_t)P * sizeof(int32_t));
-    if (int rc = ensure_workspace(b, mm_bytes + adv_bytes + fit_bytes + trd_bytes)) return rc;
-    char* base = (char*)b->ws;
+    if (int rc = ensure_workspace(b, slot, mm_bytes + adv_bytes + fit_bytes + trd_bytes)) return rc;
+    char* base = (char*)b->ws[slot];
     float* d_mm = (float*)base; float* d_adv = (float*)(base + mm_bytes);
     double* d_fit = (double*)(base + mm_bytes + adv_bytes); int32_t* d_trd = (int32_t*)(base + mm_bytes + adv_bytes + fit_bytes);
     PopArgs pm, pa;
@@ -254,13 +266,57 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
     if (mm->hidden == 256) {
         if (int rc = launch_spec256(b, pm, params->phi, params->fee_rate, d_fit, d_trd, nullptr, nullptr, st)) return rc;
     } else if (params->precision != SGMM_PRECISION_F32) {
-        if (int rc = launch_tc32(b, pm, params->phi, params->fee_rate, params->units_per_lane, d_fit, d_trd, nullptr, nullptr, st,
+        if (int rc = launch_tc32(b, pm, adv ? &pa : nullptr, params->phi, params->fee_rate, params->units_per_lane, d_fit, d_trd, nullptr, nullptr, st,
                                  tc32_mode_of(params->precision))) return rc;
     } else if (int rc = launch_rollout(b, pm, adv ? &pa : nullptr, mm->hidden, params->phi, params->fee_rate,
                                        params->units_per_lane, params->warps_per_cta, d_fit, d_trd, st)) return rc;
     if (int rc = check_cuda(cudaMemcpyAsync(fitness, d_fit, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H fitness")) return rc;
-    if (int rc = check_cuda(cudaMemcpyAsync(trades, d_trd, (size_t)P * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "D2H trades")) return rc;
+    return check_cuda(cudaMemcpyAsync(trades, d_trd, (size_t)P * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "D2H trades");
+}
+
+int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                                 const sgmm_rollout_params* params, double* fitness, int32_t* trades, void* stream)
+{
+    if (int rc = check_rollout_args(bundle, mm, adv, params, fitness, trades)) return rc;
+    if (mm->count == 0) return SGMM_OK;
+    sgmm_bundle* b = const_cast<sgmm_bundle*>(bundle);
+    std::lock_guard<std::mutex> lock(b->ws_mutex);
+    DeviceGuard guard(b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = enqueue_host_rollout(b, 0, mm, adv, params, fitness, trades, st)) return rc;
     return check_cuda(cudaStreamSynchronize(st), "rollout_population_host");
+}
+
+int sgmm_rollout_population_host_async(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                                       const sgmm_rollout_params* params, double* fitness, int32_t* trades, int32_t* ticket)
+{
+    if (!ticket) { set_error("ticket is NULL"); return SGMM_ERR_INVALID; }
+    *ticket = -1;
+    if (int rc = check_rollout_args(bundle, mm, adv, params, fitness, trades)) return rc;
+    sgmm_bundle* b = const_cast<sgmm_bundle*>(bundle);
+    std::lock_guard<std::mutex> lock(b->ws_mutex);
+    DeviceGuard guard(b->device);
+    // slots 1 .. SGMM_HOST_SLOTS-1 rotate; a slot is reused only after its previous batch has completed
+    const int slot = 1 + (int)(b->async_next++ % (SGMM_HOST_SLOTS - 1));
+    if (!b->slot_stream[slot])
+        if (int rc = check_cuda(cudaStreamCreateWithFlags(&b->slot_stream[slot], cudaStreamNonBlocking), "cudaStreamCreate(slot)")) return rc;
+    cudaStream_t st = b->slot_stream[slot];
+    if (int rc = check_cuda(cudaStreamSynchronize(st), "slot still busy")) return rc;       // its previous batch (if any) is done
+    if (mm->count > 0)
+        if (int rc = enqueue_host_rollout(b, slot, mm, adv, params, fitness, trades, st)) return rc;
+    *ticket = slot;
+    return SGMM_OK;
+}
+
+int sgmm_rollout_wait(const sgmm_bundle* bundle, int32_t ticket)
+{
+    if (!bundle || ticket < 1 || ticket >= SGMM_HOST_SLOTS) { set_error("bad bundle / ticket"); return SGMM_ERR_INVALID; }
+    sgmm_bundle* b = const_cast<sgmm_bundle*>(bundle);
+    cudaStream_t st;
+    { std::lock_guard<std::mutex> lock(b->ws_mutex); st = b->slot_stream[ticket]; }
+    if (!st) { set_error("ticket %d was never issued", ticket); return SGMM_ERR_INVALID; }
+    DeviceGuard guard(b->device);
+    return check_cuda(cudaStreamSynchronize(st), "rollout_wait");
 }
 
 int sgmm_rollout_trace(const sgmm_bundle* bundle, const float* mm_genome, int32_t hidden, const float* adv_genome,
@@ -363,7 +419,17 @@ int sgmm_env_step_host(sgmm_env_state* e, const int64_t action[2], const int64_t
     if (!e || !action || !info) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
     int64_t off_a = action[0], off_b = action[1];                        // market_env.py:23
     if (adv_action) { off_a += adv_action[0]; off_b += adv_action[1]; }  // :25-28
-    env_step(*e, off_a, off_b, mid_next, best_ask, best_bid, buy_max, sell_min, *info);
+    env_step<int64_t>(*e, off_a, off_b, mid_next, best_ask, best_bid, buy_max, sell_min, *info);
+    return SGMM_OK;
+}
+
+int sgmm_env_step_host_real(sgmm_env_state* e, const double action[2], const int64_t* adv_action, double mid_next,
+                            double best_ask, double best_bid, double buy_max, double sell_min, sgmm_step_info* info)
+{
+    if (!e || !action || !info) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
+    double off_a = action[0], off_b = action[1];                         // market_env.py:23 (offsets as given)
+    if (adv_action) { off_a = add_rn(off_a, (double)adv_action[0]); off_b = add_rn(off_b, (double)adv_action[1]); }  // :25-28
+    env_step<double>(*e, off_a, off_b, mid_next, best_ask, best_bid, buy_max, sell_min, *info);
     return SGMM_OK;
 }
 

@@ -25,14 +25,25 @@ struct GaDev {
 
 constexpr uint64_t ADV_SEED_FLIP = 0x8000000000000000ull;   // adversary noise stream (same as the oracle)
 
+// The population's results live in ONE rank-blocked buffer so that a sharded generation needs a single all-gather:
+//   block r (block_bytes each) = { double fitness[stride]; int32_t trades[stride]; pad }   individuals [r*stride, (r+1)*stride)
+// With one rank there is one block and stride = pop_size.
+struct Gather {
+    char* base; int64_t stride; int64_t block_bytes;
+    __host__ __device__ double* fit_block(int64_t r) const { return reinterpret_cast<double*>(base + r * block_bytes); }
+    __host__ __device__ int32_t* trd_block(int64_t r) const { return reinterpret_cast<int32_t*>(base + r * block_bytes + stride * 8); }
+    __device__ double fit(int64_t i) const { return fit_block(i / stride)[i % stride]; }
+    __device__ int32_t trd(int64_t i) const { return trd_block(i / stride)[i % stride]; }
+};
+
 // numpy argmax over fitness (SIGN=+1) or over -fitness (SIGN=-1): first maximum, first NaN wins
 template <int SIGN>
-__device__ int64_t block_argmax(const double* f, int64_t n, double* s_val, int64_t* s_idx)
+__device__ int64_t block_argmax(const Gather& f, int64_t n, double* s_val, int64_t* s_idx)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     double bv = 0.0; int64_t bi = -1; bool bnan = false;
     for (int64_t i = tid; i < n; i += nt) {
-        const double v = SIGN > 0 ? f[i] : -f[i];
+        const double v = SIGN > 0 ? f.fit(i) : -f.fit(i);
         const bool isn = (v != v);
         if (bi < 0) { bv = v; bi = i; bnan = isn; }
         else if (!bnan && (isn || v > bv)) { bv = v; bi = i; bnan = isn; }
@@ -63,7 +74,7 @@ __device__ int64_t block_argmax(const double* f, int64_t n, double* s_val, int64
     return r;
 }
 
-__global__ void __launch_bounds__(256) ga_tell_kernel(GaDev* st, const double* fit, const int32_t* trd, int64_t pop,
+__global__ void __launch_bounds__(256) ga_tell_kernel(GaDev* st, const Gather fit, int64_t pop,
                                                       float* mm_master, int64_t G, float* adv_master, int use_arl,
                                                       uint64_t seed)
 {
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(256) ga_tell_kernel(GaDev* st, const double* f
     }
     if (threadIdx.x == 0) {
         st->best_idx = best; st->adv_best_idx = abest;
-        st->train_f = fit[best]; st->train_trades = trd[best];
+        st->train_f = fit.fit(best); st->train_trades = fit.trd(best);
     }
 }
 
@@ -130,7 +141,9 @@ struct sgmm_ga {
     sgmm_ga_config cfg{};
     int64_t G = 0, capacity = 0;
     float* mm_master = nullptr; float* adv_master = nullptr; float* best_master = nullptr;
-    double* fit_all = nullptr; int32_t* trd_all = nullptr;
+    sgmm::Gather gather{nullptr, 0, 0}; int64_t n_blocks = 1, my_block = 0;
+    double* my_fit() const { return gather.fit_block(my_block); }          // this rank's slice: children [shard_first, +shard_count)
+    int32_t* my_trd() const { return gather.trd_block(my_block); }
     double* val_fit = nullptr; int32_t* val_trd = nullptr;
     GaDev* st = nullptr;
     double* h_train_f = nullptr; double* h_val_f = nullptr; int32_t* h_train_t = nullptr; int32_t* h_val_t = nullptr;
@@ -152,16 +165,27 @@ int sgmm_ga_create(sgmm_ga** out, const sgmm_ga_config* cfg, const float* mm_mas
 {
     if (!out || !cfg || !mm_master) { set_error("NULL argument"); return SGMM_ERR_INVALID; }
     *out = nullptr;
-    if (cfg->hidden != 32) { set_error("hidden=%d: GA rollouts are built for H=32", cfg->hidden); return SGMM_ERR_UNSUPPORTED; }
+    if (cfg->hidden != 32 && cfg->hidden != 256) { set_error("hidden=%d: GA rollouts are built for H=32 and H=256", cfg->hidden); return SGMM_ERR_UNSUPPORTED; }
+    if (cfg->hidden == 256 && cfg->precision == SGMM_PRECISION_F32) { set_error("hidden=256 runs on the tensor cores only: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 kernel is built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
     if (cfg->precision != SGMM_PRECISION_F32 && cfg->precision != SGMM_PRECISION_BF16 && cfg->precision != SGMM_PRECISION_TF32 && cfg->precision != SGMM_PRECISION_F16) { set_error("unknown precision %d", cfg->precision); return SGMM_ERR_INVALID; }
     if (cfg->precision != SGMM_PRECISION_F32 && cfg->use_arl) { set_error("the tensor-core population evaluation has no adversary path: use precision F32 with use_arl"); return SGMM_ERR_UNSUPPORTED; }
     if (cfg->pop_size <= 0 || cfg->shard_first < 0 || cfg->shard_count < 0 ||
         cfg->shard_first + cfg->shard_count > cfg->pop_size) { set_error("bad population / shard bounds"); return SGMM_ERR_INVALID; }
+    const int64_t stride = cfg->shard_stride > 0 ? cfg->shard_stride : cfg->pop_size;
+    if (cfg->shard_stride < 0 || (cfg->shard_count > 0 && cfg->shard_first % stride != 0) || cfg->shard_count > stride ||
+        (cfg->shard_stride == 0 && cfg->shard_count != cfg->pop_size)) {
+        set_error("bad shard_stride: shards are blocks of shard_stride individuals, shard_first a multiple of it, shard_count <= it "
+                  "(0 = unsharded)"); return SGMM_ERR_INVALID;
+    }
     if (cfg->use_arl && !adv_master) { set_error("use_arl needs an adversary master"); return SGMM_ERR_INVALID; }
     if (cfg->max_generations <= 0) { set_error("max_generations must be > 0"); return SGMM_ERR_INVALID; }
     sgmm_ga* ga = new (std::nothrow) sgmm_ga();
     if (!ga) { set_error("out of host memory"); return SGMM_ERR_NOMEM; }
-    ga->device = device; ga->cfg = *cfg; ga->G = genome_len(cfg->hidden); ga->capacity = cfg->pop_size + 64;
+    ga->device = device; ga->cfg = *cfg; ga->G = genome_len(cfg->hidden);
+    ga->n_blocks = (cfg->pop_size + stride - 1) / stride; ga->my_block = cfg->shard_first / stride;
+    if (ga->my_block >= ga->n_blocks) ga->my_block = ga->n_blocks - 1;     // an empty trailing shard (shard_count == 0)
+    ga->gather.stride = stride; ga->gather.block_bytes = (stride * 12 + 15) / 16 * 16;
+    ga->capacity = ga->n_blocks * ga->gather.block_bytes;
     Guard guard(device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t G = (size_t)ga->G, cap = (size_t)ga->capacity, mg = (size_t)cfg->max_generations;
@@ -169,8 +193,7 @@ int sgmm_ga_create(sgmm_ga** out, const sgmm_ga_config* cfg, const float* mm_mas
     if (!rc) rc = check_cuda(cudaMalloc(&ga->mm_master, G * sizeof(float)), "cudaMalloc");
     if (!rc) rc = check_cuda(cudaMalloc(&ga->best_master, G * sizeof(float)), "cudaMalloc");
     if (!rc) rc = check_cuda(cudaMalloc(&ga->adv_master, 1250 * sizeof(float)), "cudaMalloc");
-    if (!rc) rc = check_cuda(cudaMalloc(&ga->fit_all, cap * sizeof(double)), "cudaMalloc");
-    if (!rc) rc = check_cuda(cudaMalloc(&ga->trd_all, cap * sizeof(int32_t)), "cudaMalloc");
+    if (!rc) rc = check_cuda(cudaMalloc(&ga->gather.base, cap), "cudaMalloc");
     if (!rc) rc = check_cuda(cudaMalloc(&ga->val_fit, sizeof(double)), "cudaMalloc");
     if (!rc) rc = check_cuda(cudaMalloc(&ga->val_trd, sizeof(int32_t)), "cudaMalloc");
     if (!rc) rc = check_cuda(cudaMalloc(&ga->st, sizeof(GaDev)), "cudaMalloc");
@@ -187,8 +210,13 @@ int sgmm_ga_create(sgmm_ga** out, const sgmm_ga_config* cfg, const float* mm_mas
     if (!rc) rc = check_cuda(cudaMemcpyAsync(ga->best_master, mm_master, G * sizeof(float), cudaMemcpyHostToDevice, st), "H2D master");
     if (!rc) rc = check_cuda(cudaMemsetAsync(ga->adv_master, 0, 1250 * sizeof(float), st), "memset");
     if (!rc && adv_master) rc = check_cuda(cudaMemcpyAsync(ga->adv_master, adv_master, 1250 * sizeof(float), cudaMemcpyHostToDevice, st), "H2D adv master");
-    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->fit_all, 0, cap * sizeof(double), st), "memset");
-    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->trd_all, 0, cap * sizeof(int32_t), st), "memset");
+    // history of generations not yet run reads as zeros (sgmm_ga_history_host additionally clamps n to the generations completed)
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->h_train_f, 0, mg * sizeof(double), st), "memset");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->h_val_f, 0, mg * sizeof(double), st), "memset");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->h_train_t, 0, mg * sizeof(int32_t), st), "memset");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->h_val_t, 0, mg * sizeof(int32_t), st), "memset");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->h_sigma, 0, mg * sizeof(float), st), "memset");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ga->gather.base, 0, cap, st), "memset");
     if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "ga_create");
     if (rc) { sgmm_ga_destroy(ga); return rc; }
     *out = ga;
@@ -201,7 +229,7 @@ int sgmm_ga_destroy(sgmm_ga* ga)
     {
         Guard guard(ga->device);
         cudaFree(ga->mm_master); cudaFree(ga->adv_master); cudaFree(ga->best_master);
-        cudaFree(ga->fit_all); cudaFree(ga->trd_all); cudaFree(ga->val_fit); cudaFree(ga->val_trd);
+        cudaFree(ga->gather.base); cudaFree(ga->val_fit); cudaFree(ga->val_trd);
         cudaFree(ga->st); cudaFree(ga->h_train_f); cudaFree(ga->h_val_f); cudaFree(ga->h_train_t);
         cudaFree(ga->h_val_t); cudaFree(ga->h_sigma);
     }
@@ -209,13 +237,16 @@ int sgmm_ga_destroy(sgmm_ga* ga)
     return SGMM_OK;
 }
 
-int sgmm_ga_buffers(sgmm_ga* ga, double** fitness_slice, int32_t** trades_slice, double** fitness_all, int32_t** trades_all)
+int sgmm_ga_buffers(sgmm_ga* ga, double** fitness_slice, int32_t** trades_slice, void** gather_base,
+                    int64_t* block_bytes, int32_t* n_blocks, int32_t* my_block)
 {
     if (!ga) { set_error("ga is NULL"); return SGMM_ERR_INVALID; }
-    if (fitness_slice) *fitness_slice = ga->fit_all + ga->cfg.shard_first;
-    if (trades_slice) *trades_slice = ga->trd_all + ga->cfg.shard_first;
-    if (fitness_all) *fitness_all = ga->fit_all;
-    if (trades_all) *trades_all = ga->trd_all;
+    if (fitness_slice) *fitness_slice = ga->my_fit();
+    if (trades_slice) *trades_slice = ga->my_trd();
+    if (gather_base) *gather_base = ga->gather.base;
+    if (block_bytes) *block_bytes = ga->gather.block_bytes;
+    if (n_blocks) *n_blocks = (int32_t)ga->n_blocks;
+    if (my_block) *my_block = (int32_t)ga->my_block;
     return SGMM_OK;
 }
 
@@ -231,11 +262,14 @@ int sgmm_ga_evaluate(sgmm_ga* ga, const sgmm_bundle* train, void* stream)
     mm.first_index = c.shard_first; mm.count = c.shard_count; mm.first_index_dev = nullptr;
     PopArgs adv = mm;
     adv.master = ga->adv_master; adv.sigma_dev = &ga->st->adv_sigma; adv.seed = c.seed ^ ADV_SEED_FLIP;
+    if (c.hidden == 256)                                        // BASELINE config 4: spec256_kernel + account_kernel
+        return launch_spec256(train, mm, c.phi, c.fee_rate, ga->my_fit(), ga->my_trd(),
+                              nullptr, nullptr, (cudaStream_t)stream);
     if (c.precision != SGMM_PRECISION_F32)                      // tensor-core population evaluation (no adversary path)
-        return launch_tc32(train, mm, c.phi, c.fee_rate, 0, ga->fit_all + c.shard_first, ga->trd_all + c.shard_first,
+        return launch_tc32(train, mm, c.use_arl ? &adv : nullptr, c.phi, c.fee_rate, 0, ga->my_fit(), ga->my_trd(),
                            nullptr, nullptr, (cudaStream_t)stream, tc32_mode_of(c.precision));
     return launch_rollout(train, mm, c.use_arl ? &adv : nullptr, c.hidden, c.phi, c.fee_rate, 0, 0,
-                          ga->fit_all + c.shard_first, ga->trd_all + c.shard_first, (cudaStream_t)stream);
+                          ga->my_fit(), ga->my_trd(), (cudaStream_t)stream);
 }
 
 int sgmm_ga_select(sgmm_ga* ga, const sgmm_bundle* val, void* stream)
@@ -245,12 +279,14 @@ int sgmm_ga_select(sgmm_ga* ga, const sgmm_bundle* val, void* stream)
     Guard guard(ga->device);
     cudaStream_t st = (cudaStream_t)stream;
     const sgmm_ga_config& c = ga->cfg;
-    ga_tell_kernel<<<1, 256, 0, st>>>(ga->st, ga->fit_all, ga->trd_all, c.pop_size, ga->mm_master, ga->G,
+    ga_tell_kernel<<<1, 256, 0, st>>>(ga->st, ga->gather, c.pop_size, ga->mm_master, ga->G,
                                       ga->adv_master, c.use_arl, c.seed);
     if (int rc = check_cuda(cudaGetLastError(), "ga_tell_kernel launch")) return rc;
     PopArgs one{};
     one.genomes = ga->mm_master; one.master = nullptr; one.count = 1;          // the new master IS the best child
-    if (int rc = launch_rollout(val, one, nullptr, c.hidden, c.phi, c.fee_rate, 1, 1, ga->val_fit, ga->val_trd, st)) return rc;
+    if (c.hidden == 256) {                                                     // no exact kernel at this width: same tensor-core path
+        if (int rc = launch_spec256(val, one, c.phi, c.fee_rate, ga->val_fit, ga->val_trd, nullptr, nullptr, st)) return rc;
+    } else if (int rc = launch_rollout(val, one, nullptr, c.hidden, c.phi, c.fee_rate, 1, 1, ga->val_fit, ga->val_trd, st)) return rc;
     ga_update_kernel<<<1, 256, 0, st>>>(ga->st, ga->val_fit, ga->val_trd, ga->mm_master, ga->best_master, ga->G,
                                         c.patience, c.use_arl, c.max_generations, ga->h_train_f, ga->h_val_f,
                                         ga->h_train_t, ga->h_val_t, ga->h_sigma);
@@ -260,7 +296,7 @@ int sgmm_ga_select(sgmm_ga* ga, const sgmm_bundle* val, void* stream)
 int sgmm_ga_generation(sgmm_ga* ga, const sgmm_bundle* train, const sgmm_bundle* val, void* stream)
 {
     if (!ga) { set_error("ga is NULL"); return SGMM_ERR_INVALID; }
-    if (ga->cfg.shard_first != 0 || ga->cfg.shard_count != ga->cfg.pop_size) {
+    if (ga->n_blocks != 1 || ga->cfg.shard_count != ga->cfg.pop_size) {
         set_error("sgmm_ga_generation is the single-rank path; sharded GAs call evaluate / all-gather / select");
         return SGMM_ERR_INVALID;
     }

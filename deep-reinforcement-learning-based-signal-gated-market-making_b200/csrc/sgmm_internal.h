@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include "../../include/sgmm.h"
@@ -32,6 +33,8 @@ constexpr int32_t K_FLOAT_EXACT = 1 << 22;   // |threshold| below which Ka+0.5 i
 
 }  // namespace sgmm
 
+#define SGMM_HOST_SLOTS 3          // 1 synchronous + 2 pipelined host-buffer workspaces per bundle
+
 struct sgmm_bundle {
     int device = 0;
     int64_t T = 0;
@@ -41,15 +44,25 @@ struct sgmm_bundle {
     double* bmax = nullptr;            // [T] raw bounds (trace kernel runs the literal step core)
     double* smin = nullptr;
     uint8_t* a1 = nullptr;             // [ceil(T/25)][4096] layer-1 A operand tiles of the tensor-core H=32 path (sgmm_tc32.cu)
-    // grow-only workspace of the *_host entry points
+    // grow-only workspaces of the *_host entry points: slot 0 = the synchronous entry (caller's stream), slots 1.. = the
+    // pipelined entry (sgmm_rollout_population_host_async), each with its own stream so that the H2D copy of one batch
+    // overlaps the kernel of the previous one
     std::mutex ws_mutex;
-    void* ws = nullptr;
-    size_t ws_bytes = 0;
+    void* ws[SGMM_HOST_SLOTS] = {};
+    size_t ws_bytes[SGMM_HOST_SLOTS] = {};
+    cudaStream_t slot_stream[SGMM_HOST_SLOTS] = {};
+    uint64_t async_next = 0;
     // [count][T] 64-bit step codes of the tensor-core rollouts (sgmm_account.cu), grow-only
     std::mutex codes_mutex;
     uint64_t* codes = nullptr;
     size_t codes_cap = 0;
     std::vector<uint64_t*> codes_retired;
+    // ordering of the users of `codes` across streams: the last user's stream and an event recorded after its accounting
+    // kernel; a rollout arriving on another stream waits for it (outside stream capture)
+    cudaStream_t codes_stream = nullptr;
+    cudaEvent_t codes_done = nullptr;
+    bool codes_busy = false;
+    bool codes_captured = false;       // a stream capture has used `codes`: its address may live in a graph
 };
 
 namespace sgmm {
@@ -82,6 +95,22 @@ struct RolloutArgs {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: opt in once per (kernel, device).
+// `mask` is one static word per kernel instantiation, bit d = configured on device d (the calling thread's current
+// device).  Devices >= 64 simply re-apply the attribute on every launch.  Safe from concurrent host threads: a lost
+// race only repeats an idempotent call.
+template <typename Kernel>
+inline int opt_in_smem(Kernel kern, size_t bytes, std::atomic<uint64_t>& mask, const char* what)
+{
+    int dev = -1;
+    if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && (mask.load(std::memory_order_acquire) >> dev & 1ull)) return SGMM_OK;
+    if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what)) return rc;
+    if (tracked) mask.fetch_or(1ull << dev, std::memory_order_release);
+    return SGMM_OK;
+}
+
 int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, int hidden,
                    double phi, double fee, int units_per_lane, int warps_per_cta,
                    double* fitness, int32_t* trades, cudaStream_t st);
@@ -90,13 +119,14 @@ int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const
                  double* fitness, int32_t* trades, cudaStream_t st);
 int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades,
                    float* raw_table, int32_t* act_trace, cudaStream_t st);
-int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
+int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, double phi, double fee, int group, double* fitness, int32_t* trades,
                 float* raw_table, int32_t* act_trace, cudaStream_t st, int mode = 0);   // mode: 0 bf16, 1 tf32, 2 f16
 inline int tc32_mode_of(int precision) { return precision == SGMM_PRECISION_TF32 ? 1 : (precision == SGMM_PRECISION_F16 ? 2 : 0); }
 int launch_tc32_prologue(sgmm_bundle* b, cudaStream_t st);
 int launch_account(const sgmm_bundle* b, const uint64_t* codes, int64_t count, double phi, double fee, double* fitness,
                    int32_t* trades, cudaStream_t st, bool float_offsets = false);
 int reserve_codes(const sgmm_bundle* b, int64_t count, cudaStream_t st, uint64_t** out);
+int release_codes(const sgmm_bundle* b, cudaStream_t st);      // after the last kernel that reads the codes was enqueued
 size_t tc32_a1_bytes(int64_t T);
 int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const double* mid,
                     const double* ask, const double* bid, cudaStream_t st);

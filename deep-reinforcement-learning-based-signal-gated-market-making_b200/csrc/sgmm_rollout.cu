@@ -491,13 +491,9 @@ template <int U, bool ADV, bool FEE>
 static int launch_variant(const RolloutArgs& args, int warps, cudaStream_t st)
 {
     auto kern = rollout_kernel_h32<U, ADV, FEE>;
-    static bool configured = false;            // per instantiation
+    static std::atomic<uint64_t> configured{0};   // per instantiation, one bit per device
     const size_t smem = sizeof(RingSmem);
-    if (!configured) {
-        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                                "cudaFuncSetAttribute(smem)")) return rc;
-        configured = true;
-    }
+    if (int rc = opt_in_smem(kern, smem, configured, "cudaFuncSetAttribute(smem)")) return rc;
     const int64_t per_cta = (int64_t)warps * U;
     const int64_t blocks = (args.mm.count + per_cta - 1) / per_cta;
     kern<<<(unsigned)blocks, (warps + 1) * 32, smem, st>>>(args);   // + the producer warp

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) spec256_kernel(const Args a)
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    const PopArgs pop = a.mm;
+    const PopArgs pop = resolve(a.mm);           // GA: sigma / generation come from device scalars
     uint32_t gt = 0;                               // tiles processed so far by this CTA (pipeline phase source)
 
     for (int64_t ind = blockIdx.x; ind < pop.count; ind += gridDim.x) {
@@ -653,17 +653,14 @@ int launch_spec256(const sgmm_bundle* b, const PopArgs& mm, double phi, double f
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
     const int grid = (int)(mm.count < sms ? mm.count : sms);
     const size_t smem = sizeof(Smem) + 1024;
-    static bool configured[2] = {false, false};
+    static std::atomic<uint64_t> configured[2];       // per variant, one bit per device (zero-initialised)
     const bool has_fee = fee != 0.0;
     auto kern = has_fee ? spec256_kernel<true> : spec256_kernel<false>;
-    if (!configured[has_fee]) {
-        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                                "cudaFuncSetAttribute(spec256 smem)")) return rc;
-        configured[has_fee] = true;
-    }
+    if (int rc = opt_in_smem(kern, smem, configured[has_fee], "cudaFuncSetAttribute(spec256 smem)")) return rc;
     kern<<<grid, NUM_THREADS, smem, st>>>(a);
     if (int rc = check_cuda(cudaGetLastError(), "spec256_kernel launch")) return rc;
-    return launch_account(b, a.codes, mm.count, phi, fee, fitness, trades, st);     // the fp64 half, after the tensor-core kernel
+    if (int rc = launch_account(b, a.codes, mm.count, phi, fee, fitness, trades, st)) return rc;   // the fp64 half, after the tensor-core kernel
+    return release_codes(b, st);
 }
 
 }  // namespace sgmm

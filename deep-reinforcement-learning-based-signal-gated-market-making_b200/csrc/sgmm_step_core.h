@@ -41,12 +41,19 @@ SGMM_HD double sub_rn(double a, double b)
 #endif
 }
 
-// market_env.py:30-31
-SGMM_HD double quote_ask(double best_ask, int64_t off_a, double tick) { return add_rn(best_ask, mul_rn((double)off_a, tick)); }
-SGMM_HD double quote_bid(double best_bid, int64_t off_b, double tick) { return sub_rn(best_bid, mul_rn((double)off_b, tick)); }
+// market_env.py:30-31.  Offsets are ticks: integers from the policies (drl_engine.py:39), but the env itself takes
+// whatever the caller passes (:23) -- an unrounded benchmark offset such as 1.7 quotes at 1.7 ticks -- hence the
+// double overloads (int -> double is exact for |off| < 2^53, so both give the same quote for integral offsets).
+SGMM_HD double quote_ask(double best_ask, double off_a, double tick) { return add_rn(best_ask, mul_rn(off_a, tick)); }
+SGMM_HD double quote_bid(double best_bid, double off_b, double tick) { return sub_rn(best_bid, mul_rn(off_b, tick)); }
+SGMM_HD double quote_ask(double best_ask, int64_t off_a, double tick) { return quote_ask(best_ask, (double)off_a, tick); }
+SGMM_HD double quote_bid(double best_bid, int64_t off_b, double tick) { return quote_bid(best_bid, (double)off_b, tick); }
+SGMM_HD double quote_ask(double best_ask, int off_a, double tick) { return quote_ask(best_ask, (double)off_a, tick); }
+SGMM_HD double quote_bid(double best_bid, int off_b, double tick) { return quote_bid(best_bid, (double)off_b, tick); }
 
-// market_env.py:22-67.  off_a/off_b already include the adversary's displacement (:25-28).
-SGMM_HD void env_step(sgmm_env_state& e, int64_t off_a, int64_t off_b,
+// market_env.py:22-67.  off_a/off_b already include the adversary's displacement (:25-28).  Off = int64_t or double.
+template <typename Off>
+SGMM_HD void env_step(sgmm_env_state& e, Off off_a, Off off_b,
                       double mid_next, double best_ask, double best_bid,
                       double buy_max, double sell_min, sgmm_step_info& out)
 {

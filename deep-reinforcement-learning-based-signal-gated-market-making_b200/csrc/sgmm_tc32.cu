@@ -1001,12 +1001,13 @@ int tc32_group_size(int64_t count, int sms)
     return best;
 }
 
-int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, int group, double* fitness, int32_t* trades,
+int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, double phi, double fee, int group, double* fitness, int32_t* trades,
                 float* raw_table, int32_t* act_trace, cudaStream_t st, int mode)
 {
     using namespace tc32;
     if (mm.count == 0) return SGMM_OK;
     if (act_trace && !raw_table) { set_error("act_trace needs raw_table"); return SGMM_ERR_INVALID; }
+    if (adv) { set_error("the H=32 tensor-core rollout has no adversary path yet"); return SGMM_ERR_UNSUPPORTED; }
     Args a;
     a.sig = b->sig; a.px = b->px; a.a1 = b->a1 + (mode == M_F16 ? tc32_chunks(b->T) * A1_BYTES : 0); a.T = b->T; a.tick = b->tick; a.phi = phi; a.fee = fee;
     a.mm = mm; a.fitness = fitness; a.trades = trades; a.raw_table = raw_table; a.act_trace = act_trace;
@@ -1016,7 +1017,7 @@ int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee,
     const int64_t groups = (mm.count + a.group - 1) / a.group;
     const int grid = (int)(groups < sms ? groups : sms);
     const size_t smem = sizeof(Smem) + 128;
-    static bool configured[6] = {false, false, false, false, false, false};
+    static std::atomic<uint64_t> configured[6];       // per variant, one bit per device (zero-initialised)
     const bool has_fee = fee != 0.0;
     if (mode < 0 || mode > 2) { set_error("unknown tensor-core mode %d", mode); return SGMM_ERR_INVALID; }
     const int variant = (has_fee ? 1 : 0) + 2 * mode;
@@ -1029,11 +1030,7 @@ int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee,
         case 4: kern = tc32_kernel<false, M_F16>; break;
         default: kern = tc32_kernel<true, M_F16>; break;
     }
-    if (!configured[variant]) {
-        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                                "cudaFuncSetAttribute(tc32 smem)")) return rc;
-        configured[variant] = true;
-    }
+    if (int rc = opt_in_smem(kern, smem, configured[variant], "cudaFuncSetAttribute(tc32 smem)")) return rc;
     kern<<<grid, NUM_THREADS, smem, st>>>(a);
     return check_cuda(cudaGetLastError(), "tc32_kernel launch");
 }

@@ -67,6 +67,28 @@ def _as_f32_matrix(x, width):
     return x.contiguous()
 
 
+def _as_adv_matrix(x):
+    """Adversary genomes: the reference's AdversaryPolicy.set_weights consumes the first 74 floats of whatever vector it
+    is handed (models/model.py:52-57) -- a 1250-float TradingPolicy-sized child of the adversary evolver (:63) or a native
+    74-float AdversaryPolicy.get_weights().  Anything of at least 74 floats is accepted; the kernels read [P, 1250] rows,
+    so shorter rows are zero padded and longer ones cut."""
+    if isinstance(x, (list, tuple)):
+        x = torch.stack([torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in x])
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    x = x.to(torch.float32)
+    if x.dim() == 1:
+        x = x.reshape(1, -1)
+    n = x.shape[1]
+    if n < 74:
+        raise ValueError(f"adversary genome has {n} floats; AdversaryPolicy needs 74 (models/model.py:40-57)")
+    if n == 1250:
+        return x.contiguous()
+    out = torch.zeros(x.shape[0], 1250, dtype=torch.float32, device=x.device)
+    out[:, :min(n, 1250)] = x[:, :1250]
+    return out
+
+
 def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_rate=0.0, hidden=32,
                        units_per_lane=0, warps_per_cta=0, precision=None):
     """One episode per individual (the reference's ``pool.starmap(evaluate_individual, ...)``).
@@ -79,7 +101,7 @@ def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_ra
     G = genome_len(hidden)
     g = _as_f32_matrix(genomes, G)
     P = g.shape[0]
-    a = None if adv_genomes is None else _as_f32_matrix(adv_genomes, 1250)
+    a = None if adv_genomes is None else _as_adv_matrix(adv_genomes)
     if a is not None and a.shape[0] != P:
         raise ValueError("adversary population size differs from the market-maker population")
     L = _lib.lib()
@@ -104,6 +126,50 @@ def rollout_population(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_ra
     return fit, trd
 
 
+class PendingRollout:
+    """A batch in flight on one of the bundle's two pipelined streams (``sgmm_rollout_population_host_async``).
+    Keeps the pinned host buffers alive; ``result()`` waits and returns ``(fitness, trades)`` as numpy arrays."""
+
+    def __init__(self, bundle, ticket, keep, fit, trd):
+        self._bundle, self._ticket, self._keep, self._fit, self._trd = bundle, ticket, keep, fit, trd
+
+    def result(self):
+        if self._ticket is not None:
+            _lib.check(_lib.lib().sgmm_rollout_wait(self._bundle.handle, self._ticket))
+            self._ticket = None
+        return self._fit.numpy(), self._trd.numpy()
+
+
+def rollout_population_async(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_rate=0.0, hidden=32,
+                             precision=None, out=None) -> PendingRollout:
+    """Pipelined end-to-end evaluation of one batch of HOST genomes: H2D + kernel + D2H are enqueued on one of two
+    internal streams and the call returns at once, so the upload of the next batch overlaps this batch's kernel
+    (at most two batches in flight).  ``genomes`` should be a pinned CPU tensor (a pageable one is staged by the
+    driver and does not overlap).  ``out = (fitness f64[P], trades i32[P])`` pinned CPU tensors may be passed to be
+    reused across batches."""
+    g = _as_f32_matrix(genomes, genome_len(hidden))
+    if g.is_cuda:
+        raise ValueError("rollout_population_async takes host genomes; device genomes need no pipelining")
+    P = g.shape[0]
+    a = None if adv_genomes is None else _as_adv_matrix(adv_genomes)
+    if a is not None and (a.is_cuda or a.shape[0] != P):
+        raise ValueError("adversary genomes must be host tensors of the same population size")
+    if out is None:
+        fit = torch.empty(P, dtype=torch.float64).pin_memory()
+        trd = torch.empty(P, dtype=torch.int32).pin_memory()
+    else:
+        fit, trd = out
+        if fit.numel() != P or trd.numel() != P or fit.dtype != torch.float64 or trd.dtype != torch.int32:
+            raise ValueError("out must be (float64[P], int32[P])")
+    mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    adv = None if a is None else _lib.Population(32, 0, P, a.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    prm = _params(phi, fee_rate, 0, 0, hidden, precision)
+    ticket = C.c_int32(-1)
+    _lib.check(_lib.lib().sgmm_rollout_population_host_async(bundle.handle, C.byref(mm), None if adv is None else C.byref(adv),
+                                                            C.byref(prm), fit.data_ptr(), trd.data_ptr(), C.byref(ticket)))
+    return PendingRollout(bundle, ticket.value, (g, a), fit, trd)
+
+
 def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, first_index=0,
                    adv_master=None, adv_sigma=None, phi, fee_rate=0.0, hidden=32,
                    units_per_lane=0, warps_per_cta=0, precision=None):
@@ -121,9 +187,7 @@ def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, fi
                          int(first_index))
     advp = None
     if adv_master is not None:
-        am = torch.as_tensor(adv_master, dtype=torch.float32, device=m.device).contiguous()
-        if am.numel() != 1250:
-            raise ValueError("adversary master must have 1250 floats (models/model.py:63)")
+        am = _as_adv_matrix(torch.as_tensor(adv_master, dtype=torch.float32, device=m.device)).reshape(-1)
         adv = _lib.Population(32, 0, count, None, am.data_ptr(), float(sigma if adv_sigma is None else adv_sigma),
                               0.0, int(seed) ^ ADV_SEED_FLIP, int(generation), int(first_index))
         advp = C.byref(adv)
@@ -225,19 +289,30 @@ _BUNDLE_CACHE: "OrderedDict[tuple, Bundle]" = OrderedDict()
 _BUNDLE_CACHE_MAX = 8
 
 
+def _content_key(arrays):
+    """Cheap content fingerprint of a host bundle: lengths, dtypes and a CRC of every array's bytes (14 400 bars x 7
+    arrays = 0.7 MB: ~0.2 ms, negligible next to the upload it saves).  Keyed on content, not on ``id()``: an in-place
+    edit of a cached bundle's arrays must not silently evaluate stale device data."""
+    import zlib
+    key = []
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        key.append((a.shape, a.dtype.str, zlib.crc32(a.view(np.uint8).reshape(-1)) if a.size else 0))
+    return tuple(key)
+
+
 def _cached_bundle(bundle, train_stats, tick_size, device=None) -> Bundle:
-    """Upload a host 7-tuple once; later calls with the same arrays reuse the device copy (the
+    """Upload a host 7-tuple once; later calls with the same CONTENT reuse the device copy (the
     reference re-pickles the bundle to its workers every generation, drl_engine.py:104-115)."""
     if isinstance(bundle, Bundle):
         return bundle
     dev = torch.cuda.current_device() if device is None else int(device)
-    key = (tuple(id(a) for a in bundle), tuple(len(a) for a in bundle), float(tick_size), dev,
+    key = (_content_key(bundle), float(tick_size), dev,
            tuple((k, float(train_stats[k]), np.asarray(train_stats[k]).dtype.str)
                  for k in ("s1_m", "s1_s", "s2_m", "s2_s")))
     b = _BUNDLE_CACHE.get(key)
     if b is None:
         b = Bundle.from_arrays(bundle, train_stats, tick_size, dev)
-        b._keepalive = bundle          # ids stay unique while cached
         _BUNDLE_CACHE[key] = b
         while len(_BUNDLE_CACHE) > _BUNDLE_CACHE_MAX:
             _BUNDLE_CACHE.popitem(last=False)[1].close()
@@ -268,14 +343,14 @@ class DeviceGA:
     def __init__(self, mm_master, adv_master=None, *, pop_size, sigma, phi, fee_rate, use_arl, seed,
                  max_generations, patience=15, hidden=32, device=None, shard=None, precision=None):
         self.device = torch.cuda.current_device() if device is None else int(device)
-        first, count = (0, pop_size) if shard is None else shard
-        cfg = _lib.GaConfig(hidden, int(bool(use_arl)), pop_size, first, count, float(sigma), patience,
-                            float(phi), float(fee_rate), int(seed), int(max_generations),
-                            _precision(precision, 32))
+        first, count, stride = (0, pop_size, 0) if shard is None else shard
+        cfg = _lib.GaConfig(hidden, int(bool(use_arl)), pop_size, first, count, stride, float(sigma), patience,
+                            float(phi), float(fee_rate), int(seed) & 0xFFFFFFFFFFFFFFFF, int(max_generations),
+                            _precision(precision, hidden))
         m = np.ascontiguousarray(torch.as_tensor(mm_master).detach().cpu().numpy(), np.float32)
         a = None
         if use_arl:
-            a = np.ascontiguousarray(torch.as_tensor(adv_master).detach().cpu().numpy(), np.float32)
+            a = np.ascontiguousarray(_as_adv_matrix(torch.as_tensor(adv_master).detach().cpu()).reshape(-1).numpy(), np.float32)
         self.G = genome_len(hidden)
         self.pop_size, self.shard, self.max_generations = pop_size, (first, count), max_generations
         self._h = C.c_void_p()
@@ -284,10 +359,12 @@ class DeviceGA:
                                              _stream(self.device)))
 
     def buffers(self):
-        """(fitness_slice, trades_slice, fitness_all, trades_all) raw device addresses."""
-        p = [C.c_void_p() for _ in range(4)]
-        _lib.check(_lib.lib().sgmm_ga_buffers(self._h, *[C.byref(x) for x in p]))
-        return tuple(x.value for x in p)
+        """``(fitness_slice, trades_slice, gather_base, block_bytes, n_blocks, my_block)``: raw device addresses of
+        this rank's result slices and of the rank-blocked gather buffer (include/sgmm.h, sgmm_ga_buffers)."""
+        p = [C.c_void_p() for _ in range(3)]
+        bb, nb, mb = C.c_int64(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().sgmm_ga_buffers(self._h, *[C.byref(x) for x in p], C.byref(bb), C.byref(nb), C.byref(mb)))
+        return p[0].value, p[1].value, p[2].value, bb.value, nb.value, mb.value
 
     def evaluate(self, train: Bundle):
         _lib.check(_lib.lib().sgmm_ga_evaluate(self._h, train.handle, _stream(self.device)))
@@ -322,7 +399,9 @@ class DeviceGA:
         return mm, adv, best
 
     def history(self, n=None):
-        n = self.max_generations if n is None else int(n)
+        """History columns of the first ``n`` generations (default: the generations completed so far)."""
+        n = self.status()["generation"] if n is None else int(n)
+        n = max(0, min(n, self.max_generations))
         tf, vf = np.empty(n, np.float64), np.empty(n, np.float64)
         tt, vt = np.empty(n, np.int32), np.empty(n, np.int32)
         sg = np.empty(n, np.float32)
@@ -343,15 +422,27 @@ class DeviceGA:
 
 
 class DRLEngine:
-    """Drop-in for Env/drl_engine.py:69-178.  Same constructor, attributes and return values; the
-    generation loop runs on the device (:class:`DeviceGA`).  Extra keyword arguments (``seed``,
-    ``device``, ``patience``) expose what the reference hard-codes or leaves to the global RNG;
-    ``precision="bf16"`` evaluates the population with the tensor-core rollout (validation of the
-    best child stays on the exact fp32 kernel)."""
+    """Drop-in for Env/drl_engine.py:69-178.  Same constructor, attributes and return values; the generation loop
+    runs on the device (:class:`DeviceGA`).
+
+    * ``sigma`` is accepted and -- exactly like the reference (drl_engine.py:77,81 build ``NeuroEvolution(population_size=
+      pop_size)`` without it) -- NOT forwarded: the evolvers start at 0.05; set ``engine.mm_evolver.sigma`` to change it.
+    * Extra keyword arguments expose what the reference hard-codes or leaves to the global RNG: ``seed`` (``None`` = drawn
+      from torch's global generator at every ``train`` call, so repeated runs and phi sweeps are independent like the
+      reference's unseeded ``torch.randn``, models/model.py:69; an integer = reproducible, with the ``train`` call count
+      folded in), ``device``, ``patience`` (15, :155), ``hidden_dim`` (32 or 256, models/model.py:7), ``precision``
+      (``None`` / "f32": bit-exact population evaluation at hidden 32; "tf32" / "f16" / "bf16": tensor-core rollout;
+      hidden 256 always runs the tensor-core path).
+    * When ``torch.distributed`` is initialised with more than one rank, ``train`` shards the population over the ranks
+      (:class:`dist.ShardedGA`: one NCCL all-gather of fitness + trades per generation) -- the multi-GPU replacement of
+      the ``Pool(8).starmap`` of drl_engine.py:91,115.  Every rank returns the identical policy and history; rank 0
+      writes the checkpoint.
+    """
 
     def __init__(self, pop_size=50, sigma=0.05, phi=0.01, tick_size=0.01, fee_rate=0.0, use_arl=False,
-                 save_dir="checkpoints/drl", seed=0, device=None, patience=15, precision=None):
-        self.precision = precision      # None / "f32": bit-exact population evaluation; "bf16": tensor-core rollout
+                 save_dir="checkpoints/drl", seed=None, device=None, patience=15, precision=None, hidden_dim=32,
+                 group=None):
+        self.precision = precision
         self.phi = phi
         self.tick_size = tick_size
         self.fee_rate = fee_rate
@@ -361,40 +452,88 @@ class DRLEngine:
         self.seed = seed
         self.device = device
         self.patience = patience
-        self.mm_evolver = NeuroEvolution(population_size=pop_size, sigma=sigma)
+        self.hidden_dim = hidden_dim
+        self.group = group
+        self._train_calls = 0
+        self.mm_evolver = NeuroEvolution(population_size=pop_size, hidden_dim=hidden_dim)      # drl_engine.py:77
         if self.use_arl:
-            self.adv_evolver = NeuroEvolution(population_size=pop_size, sigma=sigma)
+            self.adv_evolver = NeuroEvolution(population_size=pop_size)                        # :81
+
+    def _run_seed(self):
+        """Philox key of this ``train`` call."""
+        call = self._train_calls
+        self._train_calls += 1
+        if self.seed is None:
+            return int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
+        # splitmix-style fold of the call counter: call 0 keeps the caller's seed verbatim
+        return (int(self.seed) + call * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
     def train(self, train_bundle, val_bundle, train_stats, generations=100, output_prefix="agent",
               log_every=5, verbose=True):
+        import torch.distributed as tdist
         dev = torch.cuda.current_device() if self.device is None else int(self.device)
         train = _cached_bundle(train_bundle, train_stats, self.tick_size, dev)
         val = _cached_bundle(val_bundle, train_stats, self.tick_size, dev)
         history = {'gen': [], 'train_f': [], 'val_f': [], 'train_trades': [], 'val_trades': []}
         save_path = os.path.join(self.save_dir, f"{output_prefix}_best_val_{self.phi}.pth")
-        ga = DeviceGA(self.mm_evolver.master_policy.get_weights(),
-                      self.adv_evolver.master_policy.get_weights() if self.use_arl else None,
-                      pop_size=self.mm_evolver.pop_size, sigma=self.mm_evolver.sigma, phi=self.phi,
-                      fee_rate=self.fee_rate, use_arl=self.use_arl, seed=self.seed,
-                      max_generations=max(1, generations), patience=self.patience, device=dev,
-                      precision=self.precision)
+        sharded = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(self.group) > 1
+        rank = tdist.get_rank(self.group) if sharded else 0
+        seed = self._run_seed()
+        if sharded:                                  # every rank must use rank 0's key (seed=None draws per process)
+            t = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=f"cuda:{dev}")
+            tdist.broadcast(t, src=tdist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            seed = int(t.item())
+        pop = self.mm_evolver.pop_size
+
+        def make(shard=None):
+            return DeviceGA(self.mm_evolver.master_policy.get_weights(),
+                            self.adv_evolver.master_policy.get_weights() if self.use_arl else None,
+                            pop_size=pop, sigma=self.mm_evolver.sigma, phi=self.phi,
+                            fee_rate=self.fee_rate, use_arl=self.use_arl, seed=seed,
+                            max_generations=max(1, generations), patience=self.patience, device=dev,
+                            precision=self.precision, hidden=self.hidden_dim, shard=shard)
+        if sharded:
+            from .dist import ShardedGA
+            runner = ShardedGA(make, pop, group=self.group)
+            ga = runner.ga
+        else:
+            runner = ga = make()
+        saved_val = -np.inf
+
+        def checkpoint(best_val):
+            """drl_engine.py:144-150 saves on every improvement; here at every poll that saw one, so that an
+            interrupted run keeps the best-on-validation master found so far."""
+            nonlocal saved_val
+            if best_val > saved_val:
+                saved_val = best_val
+                if rank == 0:
+                    _, _, best = ga.masters()
+                    snap = TradingPolicy(hidden_dim=self.hidden_dim)
+                    snap.set_weights(torch.from_numpy(best))
+                    torch.save(snap.state_dict(), save_path)
+
         try:
             logged = 0
             for gen in range(generations):
-                ga.generation(train, val)                       # ask + evaluate + tell + validate + select
-                if verbose and gen % log_every == 0:            # drl_engine.py:169-171
+                runner.generation(train, val)                   # ask + evaluate (+ all-gather) + tell + validate + select
+                if gen % log_every == 0:                        # drl_engine.py:169-171
                     h = ga.history(gen + 1)
                     best_so_far = np.maximum.accumulate(h["val_f"])
-                    for g in range(logged, gen + 1):
-                        if g > 0 and h["sigma"][g] != h["sigma"][g - 1]:
-                            print(f">>> Sigma decayed to {h['sigma'][g]:.4f} due to no improvement")
+                    checkpoint(float(best_so_far[gen]))
+                    if verbose and rank == 0:
+                        for g in range(logged, gen + 1):
+                            if g > 0 and h["sigma"][g] != h["sigma"][g - 1]:
+                                print(f">>> Sigma decayed to {h['sigma'][g]:.4f} due to no improvement")
+                        tag = "*" if (gen == 0 or h["val_f"][gen] > best_so_far[gen - 1]) else ""
+                        arl = "ARL:ON" if self.use_arl else "ARL:OFF"
+                        print(f"Gen {gen:03d} | {arl} | Best Train: {h['train_f'][gen]:.2f} | Val: {h['val_f'][gen]:.2f}{tag}")
                     logged = gen + 1
-                    tag = "*" if (gen == 0 or h["val_f"][gen] > best_so_far[gen - 1]) else ""
-                    arl = "ARL:ON" if self.use_arl else "ARL:OFF"
-                    print(f"Gen {gen:03d} | {arl} | Best Train: {h['train_f'][gen]:.2f} | Val: {h['val_f'][gen]:.2f}{tag}")
             h = ga.history(generations)
             st = ga.status()
             mm, adv, best = ga.masters()
+            improved = generations > 0 and st["best_val"] > -np.inf
+            if improved:
+                checkpoint(float(st["best_val"]))
         finally:
             ga.close()
         history['gen'] = list(range(generations))
@@ -408,8 +547,5 @@ class DRLEngine:
             self.adv_evolver.master_policy.set_weights(torch.from_numpy(adv))
         # drl_engine.py:144-150,174-176: the checkpoint holds the master of the best validation
         # generation and is loaded back into the returned policy
-        improved = generations > 0 and st["best_val"] > -np.inf
         self.mm_evolver.master_policy.set_weights(torch.from_numpy(best if improved else mm))
-        if improved:
-            torch.save(self.mm_evolver.master_policy.state_dict(), save_path)
         return self.mm_evolver.master_policy, history

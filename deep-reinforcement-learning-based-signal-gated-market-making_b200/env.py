@@ -28,7 +28,9 @@ class FTPEnv:
         self._info = _lib.StepInfo()
         self._act = (C.c_int64 * 2)()
         self._adv = (C.c_int64 * 2)()
+        self._actf = (C.c_double * 2)()
         self._step = _lib.lib().sgmm_env_step_host
+        self._step_real = _lib.lib().sgmm_env_step_host_real
         _lib.check(_lib.lib().sgmm_env_init(C.byref(self._s), float(phi), float(tick_size), float(fee_rate)))
 
     phi = _attr("phi", float)
@@ -45,14 +47,20 @@ class FTPEnv:
         return self.inventory, self.cash
 
     def step(self, action, mid_next, best_ask, best_bid, buy_max, sell_min, adv_action=None):
-        self._act[0], self._act[1] = int(action[0]), int(action[1])
+        a0, a1 = action[0], action[1]                             # market_env.py:23: offsets as given, floats included
         adv = None
         if adv_action is not None:
             d = np.round(adv_action).astype(int)                  # market_env.py:26
             self._adv[0], self._adv[1] = int(d[0]), int(d[1])
             adv = self._adv
-        _lib.check(self._step(C.byref(self._s), self._act, adv, float(mid_next), float(best_ask),
-                              float(best_bid), float(buy_max), float(sell_min), C.byref(self._info)))
+        if float(a0).is_integer() and float(a1).is_integer() and abs(a0) < 2 ** 62 and abs(a1) < 2 ** 62:
+            self._act[0], self._act[1] = int(a0), int(a1)
+            _lib.check(self._step(C.byref(self._s), self._act, adv, float(mid_next), float(best_ask),
+                                  float(best_bid), float(buy_max), float(sell_min), C.byref(self._info)))
+        else:                                                     # e.g. an unrounded GLFT offset: quote at 1.7 ticks, not 1
+            self._actf[0], self._actf[1] = float(a0), float(a1)
+            _lib.check(self._step_real(C.byref(self._s), self._actf, adv, float(mid_next), float(best_ask),
+                                       float(best_bid), float(buy_max), float(sell_min), C.byref(self._info)))
         i = self._info
         info = {'pnl_reward': i.pnl_reward, 'inventory_reward': i.inventory_reward,
                 'fee_paid': i.fee_paid, 'fill_buy': i.fill_buy, 'fill_sell': i.fill_sell}

@@ -69,10 +69,10 @@ class NeuroEvolution:
     generator) for callers that want the list of tensors; :class:`engine.DRLEngine` does not call
     it -- it regenerates children on the device from a counter-based stream instead."""
 
-    def __init__(self, population_size=50, sigma=0.05):
+    def __init__(self, population_size=50, sigma=0.05, hidden_dim=32):
         self.pop_size = population_size
         self.sigma = sigma
-        self.master_policy = TradingPolicy()
+        self.master_policy = TradingPolicy(hidden_dim=hidden_dim)       # hidden_dim: models/model.py:7 (reference: 32)
 
     def ask(self):
         base = self.master_policy.get_weights()

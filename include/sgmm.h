@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SGMM_VERSION 100            /* 0.1.0 */
+#define SGMM_VERSION 101            /* 0.1.1 */
 
 #define SGMM_OK               0
 #define SGMM_ERR_INVALID     -1     /* bad argument (NULL, negative size, unsupported hidden width) */
@@ -147,6 +147,16 @@ int sgmm_rollout_population_host(const sgmm_bundle* bundle, const sgmm_populatio
                                  const sgmm_population* adv, const sgmm_rollout_params* params,
                                  double* fitness, int32_t* trades, void* stream);
 
+/* Pipelined variant of the host-buffer entry for callers that evaluate batch after batch (a population service, or
+ * independent populations such as a phi sweep): enqueues H2D + kernel + D2H of this batch on one of two internal streams
+ * of the bundle and returns at once, so the upload of batch k+1 overlaps the kernel of batch k.  The HOST buffers
+ * (genomes in, fitness / trades out; pinned memory for true overlap) must stay untouched until sgmm_rollout_wait(ticket)
+ * returns.  At most two batches are in flight: a third call first waits for the oldest.  Same arguments otherwise. */
+int sgmm_rollout_population_host_async(const sgmm_bundle* bundle, const sgmm_population* mm,
+                                       const sgmm_population* adv, const sgmm_rollout_params* params,
+                                       double* fitness, int32_t* trades, int32_t* ticket);
+int sgmm_rollout_wait(const sgmm_bundle* bundle, int32_t ticket);
+
 /* Audit variant of the tensor-core paths (hidden = 32 or 256, SGMM_PRECISION_BF16): same kernel, plus
  *   raw_table  DEVICE float[count][T][5][2]  policy outputs for every (bar, inventory -2..2)
  *   act_trace  DEVICE int32[count][T][2]     the offsets actually taken along the walked trajectory
@@ -202,6 +212,12 @@ int sgmm_env_init(sgmm_env_state* e, double phi, double tick_size, double fee_ra
 int sgmm_env_step_host(sgmm_env_state* e, const int64_t action[2], const int64_t* adv_action,
                        double mid_next, double best_ask, double best_bid,
                        double buy_max, double sell_min, sgmm_step_info* info);
+/* The same step with REAL-valued offsets: Env/market_env.py:23,30-31 uses the caller's offsets as given, so an unrounded
+ * benchmark offset (e.g. GLFT's 1.7 ticks before rounding, Env/benchmarks.py) quotes at 1.7 ticks.  Identical to
+ * sgmm_env_step_host for integral offsets. */
+int sgmm_env_step_host_real(sgmm_env_state* e, const double action[2], const int64_t* adv_action,
+                            double mid_next, double best_ask, double best_bid,
+                            double buy_max, double sell_min, sgmm_step_info* info);
 
 /* ---------------------------------------------------------------------------------------------
  * Device-side (1,lambda) evolution: NeuroEvolution.ask/tell + the generation loop of
@@ -221,14 +237,20 @@ typedef struct {
     int64_t pop_size;         /* GLOBAL lambda (models/model.py:60)                              */
     int64_t shard_first;      /* this rank evaluates children [shard_first, shard_first+shard_count) */
     int64_t shard_count;
+    int64_t shard_stride;     /* 0 = unsharded (one rank owns the population); else the population is cut into */
+                              /* blocks of shard_stride = ceil(pop_size / ranks) individuals, shard_first is a */
+                              /* multiple of it and shard_count <= it (the last block may be short or empty)   */
     float sigma;              /* sigma_0 = 0.05 (models/model.py:61)                             */
     int32_t patience;         /* 15 (Env/drl_engine.py:155)                                      */
     double phi, fee_rate;
     uint64_t seed;
     int32_t max_generations;  /* history capacity                                                */
     int32_t precision;        /* SGMM_PRECISION_* of the POPULATION evaluation (0 = F32, bit-exact;  */
-                              /* BF16 = tensor-core rollout, use_arl must be 0).  The validation     */
-                              /* rollout of the best child always runs the exact F32 kernel.         */
+                              /* BF16 / TF32 / F16 = tensor-core rollout).  hidden = 32: the         */
+                              /* validation rollout of the best child always runs the exact F32      */
+                              /* kernel.  hidden = 256 (BASELINE config 4): precision must be a      */
+                              /* tensor-core one, population AND validation run spec256_kernel,      */
+                              /* use_arl must be 0.                                                  */
 } sgmm_ga_config;
 
 typedef struct {
@@ -243,12 +265,16 @@ typedef struct {
 int sgmm_ga_create(sgmm_ga** out, const sgmm_ga_config* cfg, const float* mm_master,
                    const float* adv_master, int device, void* stream);
 int sgmm_ga_destroy(sgmm_ga* ga);
-/* DEVICE pointers to this rank's slice of the current generation's results (length shard_count)
- * and to the full-population gather buffers (length pop_size) that sgmm_ga_select reads.  With
- * one rank the slice IS the gather buffer.  A multi-GPU caller all-gathers the slices into the
- * gather buffers between sgmm_ga_evaluate and sgmm_ga_select (NCCL). */
-int sgmm_ga_buffers(sgmm_ga* ga, double** fitness_slice, int32_t** trades_slice,
-                    double** fitness_all, int32_t** trades_all);
+/* The population's results live in ONE rank-blocked DEVICE buffer, so that a sharded generation needs a single
+ * collective:   block r = { double fitness[stride]; int32_t trades[stride]; pad to 16 B }   (block_bytes each)
+ * holds individuals [r*stride, (r+1)*stride), stride = shard_stride (or pop_size when unsharded: one block).
+ * fitness_slice / trades_slice point into this rank's block (my_block = shard_first / stride); sgmm_ga_evaluate
+ * writes them, sgmm_ga_select reads all n_blocks blocks.  A multi-GPU caller all-gathers its block IN PLACE
+ * (ncclAllGather(base + my_block*block_bytes, base, block_bytes, ncclChar) -- torch: all_gather_into_tensor on uint8
+ * views) between the two phases: one collective per generation, fitness and trade counts together.
+ * Any output pointer may be NULL. */
+int sgmm_ga_buffers(sgmm_ga* ga, double** fitness_slice, int32_t** trades_slice, void** gather_base,
+                    int64_t* block_bytes, int32_t* n_blocks, int32_t* my_block);
 /* phase 1: ask + evaluate this rank's shard on `train` */
 int sgmm_ga_evaluate(sgmm_ga* ga, const sgmm_bundle* train, void* stream);
 /* phase 2: tell + validate on `val` + keep-best + sigma decay + history; advances the generation */
@@ -298,6 +324,11 @@ int sgmm_trace_analytics(int64_t n_traces, int64_t n_steps, const double* wealth
                          double* scratch, double* out, void* stream);    /* DEVICE pointers, no sync */
 int sgmm_trace_analytics_host(int64_t n_traces, int64_t n_steps, const double* wealth, const int32_t* inventory,
                               const uint8_t* is_trade, double* out, int device, void* stream);   /* HOST pointers */
+
+/* sizeof() of the public structs as this library was compiled, for foreign-function bindings to verify their
+ * mirrors: which = 0 sgmm_population, 1 sgmm_rollout_params, 2 sgmm_trace, 3 sgmm_env_state, 4 sgmm_step_info,
+ * 5 sgmm_ga_config, 6 sgmm_ga_status; negative for an unknown index. */
+int sgmm_abi_sizeof(int which);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helper: sustained FP32 FFMA throughput of the device (TFLOP/s), the denominator of

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"libsgmm_b200.so does not export {name}"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert L.sgmm_version() == 100
+    assert L.sgmm_version() == 101
 
 
 def test_struct_layouts_match_header():
@@ -34,7 +34,12 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.RolloutParams) == 32
     assert C.sizeof(_lib.Trace) == 14 * 8
     assert C.sizeof(_lib.EnvState) == 56 and C.sizeof(_lib.StepInfo) == 40
-    assert C.sizeof(_lib.GaConfig) == 72 and C.sizeof(_lib.GaStatus) == 32
+    assert C.sizeof(_lib.GaConfig) == 80 and C.sizeof(_lib.GaStatus) == 32
+    L = _lib.lib()
+    for which, struct in enumerate((_lib.Population, _lib.RolloutParams, _lib.Trace, _lib.EnvState, _lib.StepInfo,
+                                    _lib.GaConfig, _lib.GaStatus)):
+        assert L.sgmm_abi_sizeof(which) == C.sizeof(struct), struct.__name__
+    assert L.sgmm_abi_sizeof(99) < 0
 
 
 def test_missing_library_fails_loudly(monkeypatch):
