@@ -3,11 +3,12 @@
     python oracle/stage_ref.py            # or: __graft_entry__.build(), which calls stage() when /root/reference exists
 
 The reference is pure Python: there is nothing to compile, so "building oracle/_ref" = copying, byte for byte, the three
-source files the path lives in from where they lie under /root/reference,
+source files the path lives in (plus its caller) from where they lie under /root/reference,
 
     Env/market_env.py      FTPEnv.step / reset                      
     Env/drl_engine.py      evaluate_individual, DRLEngine            (a3-a5, a8, a11)
     models/model.py        TradingPolicy, AdversaryPolicy, NeuroEvolution (a4, a6, a7, a9, a10)
+    pipeline/agent_trainer.py   the caller of the path (8b), for the drop-in proof
 
 into oracle/_ref/ together with MANIFEST.json (sha256 of every file, so a test can prove they are unmodified).  Nothing
 under oracle/_ref/ is ever committed (the reference's sources must not enter this repository's history) and the PRODUCT
@@ -22,7 +23,10 @@ import shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 DST = os.path.join(ROOT, "oracle", "_ref")
-FILES = ("Env/market_env.py", "Env/drl_engine.py", "models/model.py")
+FILES = ("Env/market_env.py", "Env/drl_engine.py", "models/model.py",
+         # the path's CALLER, staged for the drop-in proof only (tests/test_gpu_dropin_pipeline.py runs it unchanged with
+         # this repository's dropin/ shadowing Env.* and models.model); never imported by oracle/run_ref.py
+         "pipeline/agent_trainer.py")
 
 
 def _sha(path):

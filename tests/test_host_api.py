@@ -242,3 +242,57 @@ def test_benchmark_policy_tables_match_reference_actions():
     assert np.array_equal(FOICPolicy(1, 2).get_action(-1), [1, 2])
     a = GLFTPolicy(gamma=0.0001, kappa=3000, A=0.1, sigma=0.0005).get_action(1)
     assert a[0] > a[1] and a.dtype == np.float64            # long inventory skews the quotes down
+
+
+def test_ftpenv_fractional_offsets_quote_as_given():
+    """Env/market_env.py:23,30-31 uses the offsets as given, floats included: 1.7 quotes at 1.7 ticks, not at 1."""
+    import sgmm_b200
+    env = sgmm_b200.FTPEnv(phi=1e-4, tick_size=0.001, fee_rate=3e-4)
+    ask, bid, mid = 3.481, 3.480, 3.4815
+    # ask quote = 3.481 + 1.7 * 0.001 = 3.4827: fills against buy_max 3.4828, would NOT fill at int(1.7) -> 3.482 ... both fill;
+    # use a bound between the two quotes to tell them apart
+    my_ask = ask + 1.7 * 0.001
+    r, info = env.step([1.7, 5.0], mid, ask, bid, buy_max=3.4825, sell_min=float("nan"))
+    assert info["fill_sell"] == 0 and my_ask > 3.4825                # truncation to 1 tick (3.482) would have filled
+    r, info = env.step([1.7, 5.0], mid, ask, bid, buy_max=3.4828, sell_min=float("nan"))
+    assert info["fill_sell"] == 1
+    fee = my_ask * 3e-4
+    want_pnl = 0.0 + ((my_ask - mid) - fee)
+    assert info["pnl_reward"] == want_pnl and env.cash == 0.0 + (my_ask - fee) and env.inventory == -1
+    assert r == want_pnl - 1e-4 * 1
+    # integral floats and numpy integers take the integer entry and agree with the real-valued one
+    e1, e2 = sgmm_b200.FTPEnv(1e-4, 0.001, 0.0), sgmm_b200.FTPEnv(1e-4, 0.001, 0.0)
+    r1, i1 = e1.step(np.array([2, -1]), mid, ask, bid, 3.49, 3.47, adv_action=np.array([0.6, -0.4]))
+    r2, i2 = e2.step([2.0, -1.0], mid, ask, bid, 3.49, 3.47, adv_action=np.array([0.6, -0.4]))
+    assert r1 == r2 and i1 == i2 and e1.cash == e2.cash
+
+
+def test_adversary_genome_lengths_accepted():
+    from sgmm_b200.engine import _as_adv_matrix
+    import torch
+    a74 = torch.arange(74, dtype=torch.float32)
+    m = _as_adv_matrix(a74)
+    assert m.shape == (1, 1250) and torch.equal(m[0, :74], a74) and float(m[0, 74:].abs().sum()) == 0.0
+    assert _as_adv_matrix(torch.zeros(3, 1250)).shape == (3, 1250)
+    assert _as_adv_matrix([torch.zeros(2000), torch.ones(2000)]).shape == (2, 1250)
+    with pytest.raises(ValueError):
+        _as_adv_matrix(torch.zeros(73))
+
+
+def test_reference_staging_recipe():
+    """oracle/_ref holds byte-identical copies of the reference's three hot-path files (staged by build() where
+    /root/reference exists); the manifest detects any edit."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import stage_ref
+    finally:
+        sys.path.pop(0)
+    if not os.path.exists(os.path.join(stage_ref.DST, "MANIFEST.json")):
+        pytest.skip("oracle/_ref not staged in this checkout")
+    assert stage_ref.staged()
+    if os.path.isdir(stage_ref.REF):
+        for rel in stage_ref.FILES:
+            assert open(os.path.join(stage_ref.REF, rel), "rb").read() == open(os.path.join(stage_ref.DST, rel), "rb").read()
+    tracked = __import__("subprocess").run(["git", "ls-files", "oracle/_ref"], cwd=ROOT, capture_output=True, text=True).stdout
+    assert tracked.strip() == "", "reference sources must never be committed"
