@@ -97,6 +97,8 @@ SIGNATURES = {
     "sgmm_rollout_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "sgmm_rollout_spec256_audit": (C.c_int, [C.c_void_p, C.POINTER(Population), C.POINTER(RolloutParams), C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgmm_rollout_tc_audit": (C.c_int, [C.c_void_p, C.POINTER(Population), C.POINTER(Population), C.POINTER(RolloutParams),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgmm_rollout_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.POINTER(RolloutParams), C.POINTER(Trace), C.c_void_p, C.c_void_p,
                                      C.c_void_p]),

@@ -185,6 +185,7 @@ int sgmm_bundle_destroy(sgmm_bundle* b)
         for (int k = 0; k < SGMM_HOST_SLOTS; ++k) { if (b->slot_stream[k]) { cudaStreamSynchronize(b->slot_stream[k]); cudaStreamDestroy(b->slot_stream[k]); } cudaFree(b->ws[k]); }
         for (uint64_t* p : b->codes_retired) cudaFree(p);
         if (b->codes_done) cudaEventDestroy(b->codes_done);
+        for (auto& e : b->legs) { cudaFree(e.buf); cudaEventDestroy(e.ready); }
     }
     delete b;
     return SGMM_OK;
@@ -200,7 +201,6 @@ static int check_rollout_args(const sgmm_bundle* bundle, const sgmm_population* 
         if (params->precision != SGMM_PRECISION_BF16) { set_error("hidden=256 runs on the tensor cores in bf16: pass precision=SGMM_PRECISION_BF16 (the bit-exact SGMM-F32 path and the tf32 path are built for H=32)"); return SGMM_ERR_UNSUPPORTED; }
         if (adv) { set_error("the H=256 tensor-core rollout has no adversary path"); return SGMM_ERR_UNSUPPORTED; }
     } else if (mm->hidden == 32) {
-        if (params->precision != SGMM_PRECISION_F32 && adv) { set_error("the H=32 tensor-core rollout (precision BF16 / TF32) has no adversary path; use SGMM_PRECISION_F32"); return SGMM_ERR_UNSUPPORTED; }
     } else if (params->precision != SGMM_PRECISION_F32) { set_error("the tensor-core precisions need hidden=32 (BF16 / TF32) or hidden=256 (BF16)"); return SGMM_ERR_UNSUPPORTED; }
     if (adv && adv->count != mm->count) { set_error("adv.count (%lld) != mm.count (%lld): MM i meets adversary i (Env/drl_engine.py:115)", (long long)adv->count, (long long)mm->count); return SGMM_ERR_INVALID; }
     if (adv && adv->hidden != 32) { set_error("adversary genomes are 1250-float TradingPolicy(32) genomes (models/model.py:63)"); return SGMM_ERR_INVALID; }
@@ -224,18 +224,26 @@ int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm
                           params->units_per_lane, params->warps_per_cta, fitness, trades, (cudaStream_t)stream);
 }
 
+int sgmm_rollout_tc_audit(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                          const sgmm_rollout_params* params, double* fitness, int32_t* trades, float* raw_table,
+                          int32_t* act_trace, void* stream)
+{
+    if (int rc = check_rollout_args(bundle, mm, adv, params, fitness, trades)) return rc;
+    if (params->precision == SGMM_PRECISION_F32) { set_error("audit entry is for the tensor-core paths (precision BF16 / TF32 / F16)"); return SGMM_ERR_INVALID; }
+    PopArgs pm, pa;
+    if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
+    if (adv) if (int rc = fill_pop(adv, "adv", pa, 1250)) return rc;
+    DeviceGuard guard(bundle->device);
+    if (mm->hidden == 32)
+        return launch_tc32(bundle, pm, adv ? &pa : nullptr, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table,
+                           act_trace, (cudaStream_t)stream, tc32_mode_of(params->precision));
+    return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
+}
+
 int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_rollout_params* params,
                                double* fitness, int32_t* trades, float* raw_table, int32_t* act_trace, void* stream)
 {
-    if (int rc = check_rollout_args(bundle, mm, nullptr, params, fitness, trades)) return rc;
-    if (params->precision == SGMM_PRECISION_F32) { set_error("audit entry is for the tensor-core paths (precision BF16 / TF32)"); return SGMM_ERR_INVALID; }
-    PopArgs pm;
-    if (int rc = fill_pop(mm, "mm", pm, genome_len(mm->hidden))) return rc;
-    DeviceGuard guard(bundle->device);
-    if (mm->hidden == 32)
-        return launch_tc32(bundle, pm, nullptr, params->phi, params->fee_rate, params->units_per_lane, fitness, trades, raw_table, act_trace,
-                           (cudaStream_t)stream, tc32_mode_of(params->precision));
-    return launch_spec256(bundle, pm, params->phi, params->fee_rate, fitness, trades, raw_table, act_trace, (cudaStream_t)stream);
+    return sgmm_rollout_tc_audit(bundle, mm, nullptr, params, fitness, trades, raw_table, act_trace, stream);
 }
 
 // One host-buffer rollout enqueued on `st` using workspace slot `slot` of the bundle: H2D genomes, kernel(s), D2H results.

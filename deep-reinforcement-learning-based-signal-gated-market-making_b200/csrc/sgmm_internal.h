@@ -57,6 +57,10 @@ struct sgmm_bundle {
     uint64_t* codes = nullptr;
     size_t codes_cap = 0;
     std::vector<uint64_t*> codes_retired;
+    // leg tables of the tensor-core H=32 rollout (sgmm_tc32.cu): one per fee rate seen, never freed before the bundle
+    struct LegTable { double fee; void* buf; cudaEvent_t ready; cudaStream_t stream; };
+    std::mutex legs_mutex;
+    std::vector<LegTable> legs;
     // ordering of the users of `codes` across streams: the last user's stream and an event recorded after its accounting
     // kernel; a rollout arriving on another stream waits for it (outside stream capture)
     cudaStream_t codes_stream = nullptr;

@@ -24,8 +24,10 @@
 //     individuals instead of one per compute warp, and no int -> fp64 conversions or fp64 registers in the
 //     step loop).  Measured at P = 4096 x 14 400 bars: 5.25 ms with the accounting in the loop, 4.53 ms this way.
 #include <cstdio>
+#include <cstdlib>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
+#include "sgmm_adversary.cuh"
 #include "sgmm_step_core.h"
 
 namespace sgmm {
@@ -34,7 +36,6 @@ constexpr int RING_STAGES = 4;
 constexpr int CHUNK_BARS = 128;
 constexpr int MAX_WARPS = 16;
 constexpr int REC_STAGES = 2;             // chunks of step records in flight between the compute warps and the accounting warp
-constexpr float ADV_THR = 0.54930615f;   // largest fp32 y with round(tanh(y)) == 0 (tests/golden/tanh_threshold.npz)
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy helpers (raw PTX)
@@ -148,43 +149,6 @@ int launch_prologue(sgmm_bundle* b, const float* z1, const float* z2, const doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// adversary: 20-entry displacement table per individual
-//   state s = fill_sell_prev*10 + fill_buy_prev*5 + (inv+2);  entry = (da+1) | (db+1)<<2
-// ---------------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t adversary_entry(const GenomeSource& g, int s)
-{
-    // models/model.py:40-50 on x = [inv/2, fill_sell_prev, fill_buy_prev] (drl_engine.py:45)
-    const float x0 = (float)((s % 5) - 2) * 0.5f;
-    const float x1 = (float)(s / 10);
-    const float x2 = (float)((s / 5) % 2);
-    float h[12];
-#pragma unroll 1
-    for (int j = 0; j < 12; ++j) {          // setup code, once per individual: keep it small, not fast
-        float a = g.at(36 + j);
-        a = __fmaf_rn(g.at(3 * j + 0), x0, a);
-        a = __fmaf_rn(g.at(3 * j + 1), x1, a);
-        a = __fmaf_rn(g.at(3 * j + 2), x2, a);
-        h[j] = fmaxf(a, 0.0f);
-    }
-    uint32_t e = 0;
-#pragma unroll 1
-    for (int o = 0; o < 2; ++o) {
-        float a = g.at(72 + o);
-#pragma unroll 1
-        for (int k = 0; k < 12; ++k) a = __fmaf_rn(g.at(48 + 12 * o + k), h[k], a);
-        const int d = a > ADV_THR ? 1 : (a < -ADV_THR ? -1 : 0);      // round(tanh(a))
-        e |= (uint32_t)(d + 1) << (2 * o);
-    }
-    return e;
-}
-
-__device__ __forceinline__ uint32_t table_lookup(uint32_t t0, uint32_t t1, uint32_t t2, int s)
-{
-    const uint32_t w = s < 8 ? t0 : (s < 16 ? t1 : t2);
-    return (w >> ((s & 7) * 4)) & 15u;
-}
-
-// ---------------------------------------------------------------------------------------------
 // the rollout kernel (H = 32)
 // ---------------------------------------------------------------------------------------------
 // compute warps per CTA (one more warp is the producer): bounded by the register file
@@ -201,6 +165,9 @@ struct RingSmem {
     uint64_t rec_full[REC_STAGES];
     uint64_t rec_empty[REC_STAGES];
     uint64_t rec[REC_STAGES][CHUNK_BARS][32];
+#ifdef SGMM_ROLLOUT_TRACE
+    long long trace[2][64][3];
+#endif
 };
 
 template <int U, bool ADV, bool FEE>
@@ -366,6 +333,11 @@ rollout_kernel_h32(const RolloutArgs a)
     // adversary the offsets travel as the fp32 q = raw*5 they are rounded from (no conversion in this loop).
     const int slotj = warp * NI + g;                                 // this individual's lane in the accounting warp
 
+    // Two compute warps share a scheduler (warps w and w + 4).  Measured (profiles/r2_exact_phase_trace_*.log, a clock64 trace of
+    // both from the SGMM_ROLLOUT_TRACE build): their steps lock at a relative phase of 0.19 whatever the start offset, and
+    // forcing strict alternation of the layer-2 bursts with named barriers is SLOWER (4.88 vs 4.66 ms): the FMA pipe's time
+    // per pair of warp-steps (2 x ~200 cycles, FFMA2 with three register operands issues every 2.34 cycles) is conserved
+    // whatever the interleaving; both experiments were removed again.
     for (int64_t c = 0; c < nchunks; ++c) {
         const int s = (int)(c % RING_STAGES);
         mbar_wait(&sm.full[s], (uint32_t)((c / RING_STAGES) & 1));
@@ -384,8 +356,14 @@ rollout_kernel_h32(const RolloutArgs a)
 #pragma unroll
         for (int u = 0; u < U; ++u) A1[u] = __fmaf_rn(w1y[u], sg.y, __fmaf_rn(w1x[u], sg.x, b1[u]));
 
+#ifdef SGMM_ROLLOUT_TRACE
+        const bool trc = blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && c == 4;
+#endif
 #pragma unroll 1
         for (int i = 0; i < n; ++i) {
+#ifdef SGMM_ROLLOUT_TRACE
+            if (trc && i < 64) { long long t; asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(t) : "f"(inv2)); sm.trace[warp >> 2][i][0] = t; }
+#endif
             // ---- layer 1 (inventory term) + ReLU, publish h1 ------------------------------------
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -416,6 +394,9 @@ rollout_kernel_h32(const RolloutArgs a)
                     Q[u] = __ffma2_rn(w2[u][2 * k + 1], hhi, Q[u]);
                 }
             }
+#ifdef SGMM_ROLLOUT_TRACE
+            if (trc && i < 64) { long long t; asm volatile("mov.u64 %0, %%clock64; // %1 %2" : "=l"(t) : "f"(Q[U - 1].y), "f"(P[0].x)); sm.trace[warp >> 2][i][1] = t; }
+#endif
             // ---- layer 3: products, local tree, then the cross-lane tree ------------------------
             float pa[U], pb[U];
 #pragma unroll
@@ -452,6 +433,9 @@ rollout_kernel_h32(const RolloutArgs a)
                     rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
                 }
             }
+#ifdef SGMM_ROLLOUT_TRACE
+            if (trc && i < 64) { long long t; asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(t) : "f"(ra)); sm.trace[warp >> 2][i][2] = t; }
+#endif
             // ---- quantise + fill decision -------------------------------------------------------
             const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);           // raw*5.0 (drl_engine.py:39)
             const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
@@ -483,6 +467,11 @@ rollout_kernel_h32(const RolloutArgs a)
         }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&sm.empty[s]); mbar_arrive(&sm.rec_full[r]); }
+#ifdef SGMM_ROLLOUT_TRACE
+        if (trc) for (int i = 0; i < 64; ++i)
+            printf("w%d step %2d top %6lld burst_end %6lld reduced %6lld\n", warp, i, sm.trace[warp >> 2][i][0] - sm.trace[0][0][0],
+                   sm.trace[warp >> 2][i][1] - sm.trace[0][0][0], sm.trace[warp >> 2][i][2] - sm.trace[0][0][0]);
+#endif
     }
 }
 

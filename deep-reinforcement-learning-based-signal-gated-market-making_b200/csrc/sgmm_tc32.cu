@@ -14,8 +14,22 @@
 //                                             rows 2,3 = bf16 residual of W3 | b3 (lo), rest 0
 // so the CUDA cores never touch a weight: per row they only do TMEM -> cvt.rn.relu.bf16x2 -> TMEM twice,
 // then quantise (x5, round-half-even, drl_engine.py:39) and take the SPECULATIVE env step of the row's
-// (bar, inventory) (market_env.py:30-58) -> (fp64 reward, next inventory).  A walker lane per individual
-// then follows the 5-state automaton through the table (reference order fp64 reward sum).
+// (bar, inventory) (market_env.py:30-58) -> (fp64 reward, next inventory).  A walker lane per individual then follows
+// the 5-state automaton through the table (reference order fp64 reward sum).
+//
+// With the ADVERSARY (drl_engine.py:42-48) the displacement depends on (fill_sell_prev, fill_buy_prev, inventory): a
+// 20-state automaton.  E3 then does only the INTEGER half of the row's step for each of the four (fill_sell_prev,
+// fill_buy_prev) combinations (fills against the integer thresholds, next state), the walker follows the automaton and
+// MARKS the byte it visited in every bar, and the fp64 half is done for the visited rows only -- one (bar, individual)
+// pair per thread of the E3 warps, with the P&L legs from a per-bar table of the reference's exact fp64 legs
+// (tc32_legs_kernel, built once per (bundle, fee)) -- before the walker sums the rewards in bar order.
+// Measured (profiles/r2_tc32_v*_bench.log, 4096 x 14 400): the walker must stay tiny -- it is ONE warp on a scheduler it
+// shares with six busy conversion warps: doing the fp64 half of the visited rows in the walker (40 instructions per bar)
+// ran at 19 ms, the marks scheme at 4.9 ms without / 6.3 ms with the adversary, leg-table rewards for every row in E3
+// at 3.8 / 16.5 ms, against 2.4 ms for the plain path below -- which therefore stays as it was in round 1.  The
+// adversary path is correct (tests/test_gpu_tc32.py) but not faster than the exact kernel (6.3 vs 5.3 ms): without its
+// accounting it still takes 4.9 ms, with one combination instead of four 4.3 ms (profiles/r2_tc32_dbg2.log) -- the extra
+// walker -> E3 -> walker round trip per chunk stalls the D3 drain, i.e. the MMA pipeline.
 //
 // One persistent CTA per SM works on a GROUP of up to 16 individuals in lockstep over time: the A1 tile
 // of a 25-bar chunk is loaded once and multiplied with every individual's weights (a grouped GEMM:
@@ -36,8 +50,11 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
+#include "sgmm_adversary.cuh"
 #include "sgmm_step_core.h"
 
 namespace sgmm {
@@ -71,22 +88,36 @@ constexpr uint32_t S_D = 32, S_D3 = 16;
 constexpr int64_t G32 = 1250;
 // operand precision of layers 2 and 3 (layer 1 is always the bf16 split): template parameter of the kernel
 constexpr int M_BF16 = 0, M_TF32 = 1, M_F16 = 2;
-constexpr int TAB_R_STRIDE = TILE_ROWS + 1;    // doubles per individual: 258 words -> walker lanes hit distinct banks
-constexpr int TAB_N_STRIDE = TILE_BARS * 8;    // bytes per individual: 50 words -> distinct bank pairs
+constexpr int TAB_R_STRIDE = TILE_ROWS + 1;    // 8-byte entries per individual: 258 words -> walker lanes hit distinct banks
+constexpr int TAB_N_STRIDE = 520;              // bytes per individual (25 bars x 8 B without, x 20 B with the adversary):
+                                               // 130 words -> the 16 walker lanes hit distinct bank pairs
+constexpr int LEG_N = 16;                      // leg table entries per bar and side: offsets K, K-1, .., K-15 (K = fill threshold)
+
+// per-bar record of the walker's fp64 accounting: the fill thresholds and the reference's exact P&L legs
+// (market_env.py:30-31,46-48,52-54) for the LEG_N offsets at and below each threshold
+struct __align__(16) BarLegs {
+    int32_t ka1, kb1, pad0, pad1;
+    double leg_s[LEG_N];                       // (my_ask - mid_next) - my_ask*fee   at off_a = Ka - j
+    double leg_b[LEG_N];                       // (mid_next - my_bid) - my_bid*fee   at off_b = Kb - j
+};
 
 struct Smem {
     uint8_t a1[A1_STAGES][A1_BYTES];
     uint8_t b1[GMAX][B1_BYTES];
     uint8_t b2[GMAX][B2_BYTES];
     uint8_t b3[GMAX][B3_BYTES];
-    double tab_r[3][GMAX][TAB_R_STRIDE];       // reward of (bar, inventory) rows; chunk q lives in buffer q % 3
-    uint8_t tab_n[3][GMAX][TAB_N_STRIDE];      // next inventory index | traded << 3, 8 bytes per bar
+    int2 tab_k[3][GMAX][TAB_R_STRIDE];         // quantised offsets (ka, kb) of (bar, inventory) rows; chunk q lives in buffer q % 3
+    uint8_t tab_n[3][GMAX][TAB_N_STRIDE];      // next inventory index | fill_buy << 3 | fill_sell << 4: without the adversary
+                                               // 8 bytes per bar (byte = entry inventory), with it 20 bytes per bar (byte = state)
+    uint32_t adv_tab[GMAX][4];                 // the adversary's 20-entry displacement table of every individual (3 words)
+    int2 tab_th[3][TILE_BARS + 1];             // fill thresholds + 1 (ka1, kb1) of the chunk's bars, written by E3 next to the tables
     uint64_t a1_full[A1_STAGES], a1_empty[A1_STAGES];
     // per TMEM buffer.  l*_done = tcgen05.commit of the layer's MMAs: its accumulator is complete AND the A
     // operand it read (which lives where the previous layer's accumulator was) may be overwritten.
     // a2_ready = E1 wrote A2 (4 warps); l3_ready = E2 wrote A3 (4) + E3 drained the previous D3 (4).
     uint64_t l1_done[3], a2_ready[3], l2_done[3], l3_ready[3], l3_done[3];
     uint64_t tab_full[3], tab_empty[3];
+    uint64_t vis_full[3], rew_full[3];         // walker marked the visited bytes of the chunk; E3 warps wrote its rewards
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -279,7 +310,8 @@ __device__ __forceinline__ void split3(float x, float& hi, float& mid, float& lo
 struct Args {
     const BarSig* sig; const BarPx* px; const uint8_t* a1; int64_t T;
     double tick, phi, fee;
-    PopArgs mm;
+    PopArgs mm, adv;
+    const BarLegs* legs;     // [T] (tc32_legs_kernel)
     int32_t group;           // individuals per CTA group (<= GMAX)
     double* fitness; int32_t* trades;
     float* raw_table;        // optional audit output [P][T][5][2]
@@ -403,6 +435,19 @@ __device__ __forceinline__ double int_to_double(int k)
     return __dadd_rn(__hiloint2double(0x43300000, k ^ (int)0x80000000), -4503601774854144.0);
 }
 
+// The P&L leg of one filled side, the slow way: literal market_env.py:30-31,46-48,52-54 for an offset outside the bar's
+// leg table (more than LEG_N - 1 ticks inside the fill threshold, or an always-filling bar).
+__device__ __noinline__ double slow_leg(bool sell, const BarPx* px, int k, double tick, double fee)
+{
+    const double best = sell ? px->ask : px->bid, mid = px->mid_next;
+    if (sell) {
+        const double my_ask = add_rn(best, mul_rn(int_to_double(k), tick));
+        return sub_rn(sub_rn(my_ask, mid), mul_rn(my_ask, fee));
+    }
+    const double my_bid = sub_rn(best, mul_rn(int_to_double(k), tick));
+    return sub_rn(sub_rn(mid, my_bid), mul_rn(my_bid, fee));
+}
+
 // One 25-bar chunk of one individual's walk through the table.
 //   phase A: the 5-state automaton alone (a 2-instruction integer chain per bar), remembering the inventory
 //            each bar was entered with;
@@ -410,7 +455,7 @@ __device__ __forceinline__ double int_to_double(int k)
 //            not depend on the running sum, so only the fp64 add chain is serial.
 // FULL = all 25 bars present (no per-bar predicates).
 template <bool FULL>
-__device__ __forceinline__ void walk_chunk(const uint8_t* nb, const double* rb, int n, int& iv, int& trades, double& total)
+__device__ __forceinline__ void walk_chunk_plain(const uint8_t* nb, const double* rb, int n, int& iv, int& trades, double& total)
 {
     uint32_t es[TILE_BARS], ivs[TILE_BARS];
     uint32_t w = (uint32_t)iv;
@@ -431,6 +476,38 @@ __device__ __forceinline__ void walk_chunk(const uint8_t* nb, const double* rb, 
             total = add_rn(total, rb[s * 5 + ivs[s]]);
         }
     }
+}
+
+// Phase A of one 25-bar chunk of one individual's walk: the automaton alone (a short integer chain per bar: 5 states,
+// or 20 with the adversary).  The byte visited in every bar is marked (bit 7) for the accounting threads, trades are
+// counted here (drl_engine.py:60-61).  FULL = all 25 bars present.  `st` = inventory index (0..4), with the adversary
+// the state index fill_sell_prev*10 + fill_buy_prev*5 + inventory index.
+template <bool ADV, bool FULL>
+__device__ __forceinline__ void walk_chunk(uint8_t* nb, int n, int& st, int& trades)
+{
+    uint32_t cur = (uint32_t)st;
+    int tr = 0;
+#pragma unroll
+    for (int s = 0; s < TILE_BARS; ++s) {
+        if (FULL || s < n) {
+            uint32_t e;
+            if (!ADV) {
+                const uint2 x = *reinterpret_cast<const uint2*>(nb + s * 8);
+                e = __byte_perm(x.x, x.y, cur);        // byte `cur` of the bar's 8-byte record
+                nb[s * 8 + cur] = (uint8_t)(e | 0x80u);
+                cur = e & 7u;
+            } else {
+                // with the adversary the byte holds the NEXT STATE itself (5 bits) | fill_buy << 5 | fill_sell << 6: one byte
+                // load at a data-dependent address per bar (latency, not instructions: the walker is short of issue slots)
+                e = nb[s * 20 + cur];
+                nb[s * 20 + cur] = (uint8_t)(e | 0x80u);
+                cur = e & 31u;
+            }
+            tr += (e & (ADV ? 0x60u : 0x18u)) ? 1 : 0;
+        }
+    }
+    st = (int)cur;
+    trades += tr;
 }
 
 // position of a unit in the pipeline: TMEM buffer (unit index mod 3) and mbarrier phase parity (use count & 1)
@@ -482,7 +559,7 @@ struct Ctx {
                                          // buffer is a compile-time constant of the unrolled issuer loops
     int G, lane, quarter;
     int64_t grp, T, count;
-    const BarSig* sig; const BarPx* px; const uint8_t* a1;
+    const BarSig* sig; const BarPx* px; const uint8_t* a1; const BarLegs* legs;
     double tick, phi, fee;
     double* fitness; int32_t* trades; float* raw_table; int32_t* act_trace;
 };
@@ -699,12 +776,12 @@ __device__ __noinline__ void convert_role(const Ctx& cx, uint32_t set)
     }
 }
 
-// E3: D3 -> offsets -> speculative env step of every (bar, inventory) row -> table.  Set s (four warps) owns TMEM
+// PLAIN path (no adversary), as measured in round 1 -- E3: D3 -> offsets -> speculative env step of every (bar, inventory) row -> table.  Set s (four warps) owns TMEM
 // buffer s, i.e. the units with (global unit index % 3) == s: consecutive uses of its barriers, so every parity
 // wait is at most one phase away.  Outer loop over chunks (bar data, table buffer), inner loop over the set's
 // units of the chunk.
 template <bool FEE>
-__device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
+__device__ __noinline__ void e3_role_plain(const Ctx& cx, uint32_t e3set)
 {
     Smem& sm = *cx.sm;
     const int lane = cx.lane;
@@ -745,7 +822,7 @@ __device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
         const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
         mbar_wait_a_(cx, BAR(tab_empty, cbuf), ((q / 3u) & 1u) ^ 1u);                // walker has left this table buffer
         const uint32_t tab_full = BAR(tab_full, cbuf);
-        double* tr = &sm.tab_r[cbuf][up * 2u][row];
+        double* tr = reinterpret_cast<double*>(&sm.tab_k[cbuf][up * 2u][row]);
         uint8_t* tn = &sm.tab_n[cbuf][up * 2u][tl * 8 + iv];
 #pragma unroll 1
         for (; up < UG; up += NBUF, par ^= 1u, tr += 2 * NBUF * TAB_R_STRIDE, tn += 2 * NBUF * TAB_N_STRIDE) {
@@ -822,7 +899,7 @@ __device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
 }
 
 // walker: one lane per individual of the group
-__device__ __noinline__ void walker_role(const Ctx& cx)
+__device__ __noinline__ void walker_role_plain(const Ctx& cx)
 {
     Smem& sm = *cx.sm;
     const int g = cx.lane;
@@ -839,11 +916,11 @@ __device__ __noinline__ void walker_role(const Ctx& cx)
             const int64_t t0 = (int64_t)c * TILE_BARS;
             const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
             const uint8_t* nb = sm.tab_n[cbuf][g];
-            const double* rb = sm.tab_r[cbuf][g];
-            if (n == TILE_BARS && !cx.act_trace) walk_chunk<true>(nb, rb, n, iv, trades, total);      // every chunk but the last
+            const double* rb = reinterpret_cast<const double*>(sm.tab_k[cbuf][g]);
+            if (n == TILE_BARS && !cx.act_trace) walk_chunk_plain<true>(nb, rb, n, iv, trades, total);      // every chunk but the last
             else {
                 const int iv0 = iv;
-                walk_chunk<false>(nb, rb, n, iv, trades, total);
+                walk_chunk_plain<false>(nb, rb, n, iv, trades, total);
                 if (cx.act_trace) {                                    // audit: the offsets taken (second pass over the automaton)
                     int w = iv0;
                     for (int s = 0; s < n; ++s) {
@@ -860,13 +937,267 @@ __device__ __noinline__ void walker_role(const Ctx& cx)
         if (cx.lane == 0) mbar_arrive_a(BAR(tab_empty, cbuf));
     }
     if (live) {
-        trades >>= 3;                                                  // walk_chunk counts in units of 8
+        trades >>= 3;                                                  // walk_chunk_plain counts in units of 8
         if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
         cx.fitness[ind] = total; cx.trades[ind] = trades;
     }
 }
 
-template <bool FEE, int MODE>
+// The fp64 half of the env step for the rows the walker visited in chunk c, one (bar, individual) pair per thread of
+// the twelve E3 warps: find the marked byte of the pair's bar record (-> the state the bar was entered with, fills, next
+// inventory), the offsets of that row, the adversary's displacement, the legs of the sides that filled from the bar's
+// leg table (market_env.py:30-31,44-55) and reward = pnl - phi*|inventory| (:57-58), stored as a double over the bar's
+// first row of the offset table (dead by now) for the walker's bar-order sum.
+template <bool ADV>
+__device__ __forceinline__ void account_chunk(const Ctx& cx, uint32_t c, const double (&pens)[3])
+{
+    Smem& sm = *cx.sm;
+    const uint32_t q = cx.gc + c, cbuf = q % 3u;
+    mbar_wait_a_(cx, BAR(vis_full, cbuf), (q / 3u) & 1u);
+    const int64_t t0 = (int64_t)c * TILE_BARS;
+    const int n = (int)(cx.T - t0 < TILE_BARS ? cx.T - t0 : TILE_BARS);
+    const int a = ((int)(threadIdx.x >> 5) - WARP_E3) * 32 + cx.lane;
+    const int npairs = cx.G * TILE_BARS;
+    for (int p = a; p < npairs; p += 12 * 32) {
+        const int g = p / TILE_BARS, s = p - g * TILE_BARS;
+        const int64_t ind = cx.grp * cx.G + g;
+        if (s >= n || ind >= cx.count) continue;
+        uint32_t idx, e;
+        if (!ADV) {
+            const uint2 x = *reinterpret_cast<const uint2*>(&sm.tab_n[cbuf][g][s * 8]);
+            const uint32_t m0 = x.x & 0x80808080u;
+            idx = m0 ? (uint32_t)(__ffs((int)m0) - 1) >> 3 : 4u;
+            e = __byte_perm(x.x, x.y, idx) & 0x7Fu;
+        } else {
+            const uint32_t* x = reinterpret_cast<const uint32_t*>(&sm.tab_n[cbuf][g][s * 20]);
+            uint32_t w = 0, wi = 0;
+#pragma unroll
+            for (int i = 4; i >= 0; --i) { const uint32_t v = x[i]; if (v & 0x80808080u) { w = v; wi = (uint32_t)i; } }
+            const uint32_t b = (uint32_t)(__ffs((int)(w & 0x80808080u)) - 1) >> 3;
+            idx = wi * 4u + b;
+            e = (w >> (8u * b)) & 0x7Fu;
+        }
+        const bool fb = (e & (ADV ? 32u : 8u)) != 0, fs = (e & (ADV ? 64u : 16u)) != 0;
+        const int iv_in = ADV ? (int)(idx % 5u) : (int)idx;
+        const int niv = ADV ? (int)((e & 31u) % 5u) : (int)(e & 7u);
+        int2 k = sm.tab_k[cbuf][g][s * 5 + iv_in];
+        if (cx.act_trace) { int32_t* at = cx.act_trace + ((int64_t)ind * cx.T + t0 + s) * 2; at[0] = k.x; at[1] = k.y; }   // audit: the offsets taken
+        if (ADV) {
+            const uint32_t d = table_lookup(sm.adv_tab[g][0], sm.adv_tab[g][1], sm.adv_tab[g][2], (int)idx);
+            k.x += (int)(d & 3u) - 1; k.y += (int)(d >> 2) - 1;                      // market_env.py:26-28
+        }
+        const int2 th = sm.tab_th[cbuf][s];
+        const BarLegs* L = cx.legs + t0 + s;
+        double lb = 0.0, ls = 0.0;
+        if (fb) {                                                                      // :44-49
+            const long long j = (long long)th.y - 1 - k.y;
+            lb = (unsigned long long)j < (unsigned long long)LEG_N ? __ldg(&L->leg_b[j]) : slow_leg(false, cx.px + t0 + s, k.y, cx.tick, cx.fee);
+        }
+        if (fs) {                                                                      // :50-55
+            const long long j = (long long)th.x - 1 - k.x;
+            ls = (unsigned long long)j < (unsigned long long)LEG_N ? __ldg(&L->leg_s[j]) : slow_leg(true, cx.px + t0 + s, k.x, cx.tick, cx.fee);
+        }
+        // pnl = 0.0 (+ leg_b) (+ leg_s) in the reference's order (:40,:48,:54); 0.0 + leg == leg (a leg is never -0.0)
+        const double pnl = fb ? (fs ? add_rn(lb, ls) : lb) : ls;
+        const int ai = abs(niv - 2);
+        const double pen = ai == 0 ? pens[0] : (ai == 1 ? pens[1] : pens[2]);
+        *reinterpret_cast<double*>(&sm.tab_k[cbuf][g][s * 5]) = sub_rn(pnl, pen);      // :58
+    }
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive_a(BAR(rew_full, cbuf));
+}
+
+// E3: D3 -> offsets -> the INTEGER half of the speculative env step of every (bar, inventory) row -> tables.  Set s
+// (four warps) owns TMEM buffer s, i.e. the units with (global unit index % 3) == s: consecutive uses of its barriers,
+// so every parity wait is at most one phase away.  Outer loop over chunks (bar thresholds, table buffer), inner loop
+// over the set's units of the chunk.  With the adversary the row's fills are decided for each of the four
+// (fill_sell_prev, fill_buy_prev) combinations (drl_engine.py:42-48: the displacement depends on them and on the inventory).
+template <bool ADV>
+__device__ __noinline__ void e3_role(const Ctx& cx, uint32_t e3set)
+{
+    Smem& sm = *cx.sm;
+    const int lane = cx.lane;
+    const int row = cx.quarter * 32 + lane;
+    const int tl = row / 5, iv = row % 5;            // bar within the chunk, inventory index (inv+2)
+    const bool row_ok = row < TILE_BARS * 5;
+    const int64_t T = cx.T;
+    const uint32_t nchunks = cx.nchunks, UG = cx.UG, gc = cx.gc, gt = cx.gt;
+    const BarSig* sig = cx.sig;
+    int2 kth = make_int2(0, 0), kth_n = make_int2(0, 0);
+    auto load_bar = [&](uint32_t c, int2& k) {
+        const int64_t t = (int64_t)c * TILE_BARS + tl;
+        if (row_ok && t < T) k = __ldg(reinterpret_cast<const int2*>(&sig[t].ka1));
+    };
+    const uint32_t taddr = cx.lane_addr + C_R3 + e3set * BUF_COLS;
+    const uint32_t l3_done = BAR(l3_done, e3set), l3_ready = BAR(l3_ready, e3set);
+    uint32_t par = (gt / NBUF) & 1u;                                            // cx.gt is a multiple of NBUF
+    uint32_t base3 = 0;                                                         // (index of the chunk's first unit) % 3
+    const uint32_t ug3 = UG % NBUF;
+    const int inv = iv - 2;
+    const bool leader = lane == 0;
+    const bool can_buy = inv < 2, can_sell = inv > -2;                          // market_env.py:34-35
+    const double pens[3] = {mul_rn(cx.phi, 0.0), mul_rn(cx.phi, 1.0), mul_rn(cx.phi, 2.0)};       // phi * |inventory|, market_env.py:57
+    if (nchunks > 0) load_bar(0, kth_n);
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        kth = kth_n;
+        if (c + 1 < nchunks) load_bar(c + 1, kth_n);                            // prefetch the next chunk's thresholds
+        uint32_t up = e3set >= base3 ? e3set - base3 : e3set + NBUF - base3;    // first unit of the chunk that is ours
+        base3 += ug3; if (base3 >= NBUF) base3 -= NBUF;
+        if (up >= UG) { if (c >= 1) account_chunk<ADV>(cx, c - 1, pens); continue; }     // (groups of 2 or 4: not every chunk has a unit of ours)
+        const uint32_t q = gc + c, cbuf = q % 3u;
+        const bool valid = row_ok && ((int64_t)c * TILE_BARS + tl < T);
+        mbar_wait_a_(cx, BAR(tab_empty, cbuf), ((q / 3u) & 1u) ^ 1u);                // walker has left this table buffer
+        const uint32_t tab_full = BAR(tab_full, cbuf);
+        if (row_ok && iv == 0) sm.tab_th[cbuf][tl] = kth;                       // every set writes the same values: benign
+        int2* tk = &sm.tab_k[cbuf][up * 2u][row];
+        uint8_t* tn = &sm.tab_n[cbuf][up * 2u][ADV ? tl * 20 + iv : tl * 8 + iv];
+        const uint32_t* advt = &sm.adv_tab[up * 2u][0];
+#pragma unroll 1
+        for (; up < UG; up += NBUF, par ^= 1u, tk += 2 * NBUF * TAB_R_STRIDE, tn += 2 * NBUF * TAB_N_STRIDE, advt += 2 * NBUF * 4) {
+            mbar_wait_a_(cx, l3_done, par);
+            tc_fence_after();
+            uint32_t v[2][4];
+            tmem_ld4(taddr, v[0]);
+            tmem_ld4(taddr + S_D3, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (leader) mbar_arrive_a(l3_ready);                                 // accumulator drained
+            // Both tiles of the unit, branch-free.  Rows that are not valid compute on stale thresholds and store nothing.
+            float ra[2], rb[2]; int ka[2], kb[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                ra[j] = __fadd_rn(__uint_as_float(v[j][0]), __uint_as_float(v[j][2]));       // hi + lo halves of W3
+                rb[j] = __fadd_rn(__uint_as_float(v[j][1]), __uint_as_float(v[j][3]));
+                ka[j] = max(min(quantise(__fmul_rn(ra[j], 5.0f)), K_CLAMP), -K_CLAMP);        // drl_engine.py:39
+                kb[j] = max(min(quantise(__fmul_rn(rb[j], 5.0f)), K_CLAMP), -K_CLAMP);
+            }
+            if (!ADV) {
+                uint32_t e[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool fb = can_buy && (kb[j] < kth.y);                  // market_env.py:34,37
+                    const bool fs = can_sell && (ka[j] < kth.x);                 // :35,:38
+                    e[j] = (uint32_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0)) | (fb ? 8u : 0u) | (fs ? 16u : 0u);      // :45,:51
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { tk[j * TAB_R_STRIDE] = make_int2(ka[j], kb[j]); tn[j * TAB_N_STRIDE] = (uint8_t)e[j]; }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 at = *reinterpret_cast<const uint4*>(advt + j * 4);
+                    uint32_t e[4];
+#pragma unroll
+                    for (int cmb = 0; cmb < 4; ++cmb) {                          // cmb = fill_sell_prev*2 + fill_buy_prev
+                        const uint32_t d = table_lookup(at.x, at.y, at.z, cmb * 5 + iv);
+                        const int oa = ka[j] + (int)(d & 3u) - 1, ob = kb[j] + (int)(d >> 2) - 1;    // :26-28
+                        const bool fb = can_buy && (ob < kth.y);
+                        const bool fs = can_sell && (oa < kth.x);
+                        e[cmb] = (uint32_t)((fs ? 10 : 0) + (fb ? 5 : 0) + iv + (fb ? 1 : 0) - (fs ? 1 : 0)) | (fb ? 32u : 0u) | (fs ? 64u : 0u);
+                    }
+                    if (valid) {
+                        tk[j * TAB_R_STRIDE] = make_int2(ka[j], kb[j]);
+#pragma unroll
+                        for (int cmb = 0; cmb < 4; ++cmb) tn[j * TAB_N_STRIDE + cmb * 5] = (uint8_t)e[cmb];
+                    }
+                }
+            }
+            if (valid && cx.raw_table) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t ind = cx.grp * cx.G + (int64_t)(up * 2u) + j;
+                    if (ind < cx.count) {
+                        float* o = cx.raw_table + (((int64_t)ind * T + (int64_t)c * TILE_BARS + tl) * 5 + iv) * 2;
+                        __stcg(o, ra[j]); __stcg(o + 1, rb[j]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (leader) mbar_arrive_a(tab_full);
+        }
+        // the fp64 half of the PREVIOUS chunk's visited rows (the walker has marked them by now), all E3 warps
+        if (c >= 1) account_chunk<ADV>(cx, c - 1, pens);
+    }
+    if (nchunks >= 1) account_chunk<ADV>(cx, nchunks - 1, pens);
+    // pad units of the group (at most two, one per set): drain the accumulator so that the barrier phases stay in step
+    for (uint32_t it = cx.nunits; it < cx.nunits_p; ++it) {
+        if (it % NBUF != e3set) continue;
+        mbar_wait_a_(cx, l3_done, par);
+        tc_fence_after();
+        uint32_t v[4];
+        tmem_ld4(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (leader) mbar_arrive_a(l3_ready);
+        par ^= 1u;
+    }
+}
+
+// walker: one lane per individual of the group.  Per chunk: the automaton (phase A, marks the visited bytes), then --
+// one chunk behind, when the E3 warps have turned the marks into rewards -- the reference-order fp64 sum.
+template <bool ADV>
+__device__ __noinline__ void walker_role(const Ctx& cx)
+{
+    Smem& sm = *cx.sm;
+    const int g = cx.lane;
+    const int64_t ind = cx.grp * cx.G + g, T = cx.T;
+    const bool live = g < cx.G && ind < cx.count;
+    const uint32_t nchunks = cx.nchunks, gc = cx.gc;
+    int st = 2, trades = 0;                                       // inventory 0, no previous fills
+    double total = 0.0;                                           // drl_engine.py:26
+    auto sum_chunk = [&](uint32_t c) {
+        const uint32_t q = gc + c, cbuf = q % 3u;
+        mbar_wait_a_(cx, BAR(rew_full, cbuf), (q / 3u) & 1u);
+        if (live) {
+            const int64_t t0 = (int64_t)c * TILE_BARS;
+            const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
+            const double* rw = reinterpret_cast<const double*>(&sm.tab_k[cbuf][g][0]);
+            if (n == TILE_BARS) {
+#pragma unroll
+                for (int s = 0; s < TILE_BARS; ++s) total = add_rn(total, rw[s * 5]);          // drl_engine.py:54
+            } else {
+                for (int s = 0; s < n; ++s) total = add_rn(total, rw[s * 5]);
+            }
+        }
+        __syncwarp();
+        if (cx.lane == 0) mbar_arrive_a(BAR(tab_empty, cbuf));
+    };
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t q = gc + c, cbuf = q % 3u, cpar = (q / 3u) & 1u;
+        {   // pull the next chunk's leg records (25 x 272 B) into L1 for the accounting threads
+            const int64_t tn0 = (int64_t)(c + 1) * TILE_BARS;
+            if (tn0 < T) {
+                const int64_t nb_ = T - tn0 < TILE_BARS ? T - tn0 : TILE_BARS;
+                const char* p0 = reinterpret_cast<const char*>(cx.legs + tn0);
+                for (int64_t off = (int64_t)cx.lane * 128; off < nb_ * (int64_t)sizeof(BarLegs); off += 32 * 128)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + off));
+            }
+        }
+        mbar_wait_a_(cx, BAR(tab_full, cbuf), cpar);
+        if (live) {
+            const int64_t t0 = (int64_t)c * TILE_BARS;
+            const int n = (int)(T - t0 < TILE_BARS ? T - t0 : TILE_BARS);
+            uint8_t* nb = sm.tab_n[cbuf][g];
+            if (n == TILE_BARS) walk_chunk<ADV, true>(nb, n, st, trades);          // every chunk but the last
+            else walk_chunk<ADV, false>(nb, n, st, trades);
+        }
+        __syncwarp();
+        if (cx.lane == 0) mbar_arrive_a(BAR(vis_full, cbuf));
+        if (c >= 1) sum_chunk(c - 1);
+    }
+    if (nchunks >= 1) sum_chunk(nchunks - 1);
+    if (live) {
+        if (trades == 0) total = sub_rn(total, 50.0);                 // drl_engine.py:64-65
+        cx.fitness[ind] = total; cx.trades[ind] = trades;
+    }
+}
+
+template <bool ADV, bool FEE, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -885,7 +1216,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
             mbar_init(&sm.l1_done[i], 1); mbar_init(&sm.a2_ready[i], 4);
             mbar_init(&sm.l2_done[i], 1); mbar_init(&sm.l3_ready[i], 8); mbar_init(&sm.l3_done[i], 1);
         }
-        for (int i = 0; i < 3; ++i) { mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&sm.tab_full[i], 4u * UG); mbar_init(&sm.tab_empty[i], 1);
+            mbar_init(&sm.vis_full[i], 1); mbar_init(&sm.rew_full[i], 12);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_L1) {
@@ -917,12 +1251,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
     tc_fence_after();
 
     const PopArgs pop = resolve(a.mm);
+    const PopArgs advpop = ADV ? resolve(a.adv) : a.adv;
     Ctx cx;
     cx.sm = &sm; cx.sm_addr = smem_u32(&sm); cx.tmem_base = tmem_base; cx.lane_addr = lane_addr;
     cx.gt = 0; cx.gc = 0; cx.nchunks = nchunks; cx.UG = UG; cx.nunits = nunits;
     cx.nunits_p = (nunits + NBUF - 1) / NBUF * NBUF;
     cx.G = G; cx.lane = lane; cx.quarter = quarter; cx.T = T; cx.count = pop.count;
-    cx.sig = a.sig; cx.px = a.px; cx.a1 = a.a1; cx.tick = a.tick; cx.phi = a.phi; cx.fee = a.fee;
+    cx.sig = a.sig; cx.px = a.px; cx.a1 = a.a1; cx.legs = a.legs; cx.tick = a.tick; cx.phi = a.phi; cx.fee = a.fee;
     cx.fitness = a.fitness; cx.trades = a.trades; cx.raw_table = a.raw_table; cx.act_trace = a.act_trace;
 
     for (int64_t grp = blockIdx.x; grp * G < pop.count; grp += gridDim.x) {
@@ -949,16 +1284,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc32_kernel(const Args a)
                 for (int i = 0; i < n; ++i) scatter_weight<MODE>(sm, g, e0 + i, v[i]);
             }
         }
+        if (ADV) {
+            // the adversary of every individual of the group as its 20-entry displacement table (sgmm_adversary.cuh)
+            if (tid < GMAX * 4) (&sm.adv_tab[0][0])[tid] = 0u;
+            __syncthreads();
+            for (int task = tid; task < G * 20; task += NUM_THREADS) {
+                const int g = task / 20, st = task % 20;
+                const int64_t ind = grp * G + g;
+                uint32_t e = 5u;                                       // (0, 0)
+                if (ind < pop.count) e = adversary_entry(make_source(advpop, ind, G32), st);
+                atomicOr(&sm.adv_tab[g][st >> 3], e << ((st & 7) * 4));
+            }
+        }
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
         cx.grp = grp;
         if (warp < WARP_E3) convert_role<MODE>(cx, (uint32_t)warp >> 2);
-        else if (warp < WARP_L1) e3_role<FEE>(cx, e3set);
+        else if (warp < WARP_L1) { if (ADV) e3_role<true>(cx, e3set); else e3_role_plain<FEE>(cx, e3set); }
         else if (warp == WARP_L1) l1_role<MODE>(cx);
         else if (warp == WARP_L2) issue_role<2, MODE>(cx);
         else if (warp == WARP_L3) issue_role<3, MODE>(cx);
-        else walker_role(cx);
+        else if (ADV) walker_role<true>(cx);
+        else walker_role_plain(cx);
 
         cx.gt += cx.nunits_p;
         cx.gc += nchunks;
@@ -1001,34 +1349,106 @@ int tc32_group_size(int64_t count, int sms)
     return best;
 }
 
+// The walker's per-bar records: thresholds + the reference's exact fp64 legs for the LEG_N offsets at and below each
+// threshold (one thread per (bar, side, j)); fee terms always evaluated, like the reference does with fee_rate = 0.
+__global__ void tc32_legs_kernel(int64_t T, const BarSig* __restrict__ sig, const BarPx* __restrict__ px, double tick, double fee,
+                                 tc32::BarLegs* __restrict__ legs)
+{
+    using namespace tc32;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * 2 * LEG_N) return;
+    const int64_t t = idx / (2 * LEG_N);
+    const int r = (int)(idx % (2 * LEG_N)), side = r / LEG_N, j = r % LEG_N;
+    const int32_t k1 = side == 0 ? sig[t].ka1 : sig[t].kb1;
+    if (r == 0) { legs[t].ka1 = sig[t].ka1; legs[t].kb1 = sig[t].kb1; legs[t].pad0 = legs[t].pad1 = 0; }
+    double leg = 0.0;
+    if (k1 != K_NEVER && k1 != K_ALWAYS) {                          // (never-filling bars need no legs; always-filling ones take the slow path)
+        const long long k = (long long)k1 - 1 - j;
+        if (k >= -(long long)K_CLAMP - 1 && k <= (long long)K_CLAMP + 1) {
+            const BarPx p = px[t];
+            if (side == 0) {
+                const double my_ask = add_rn(p.ask, mul_rn(int_to_double((int)k), tick));          // market_env.py:30
+                leg = sub_rn(sub_rn(my_ask, p.mid_next), mul_rn(my_ask, fee));                     // :52,:54
+            } else {
+                const double my_bid = sub_rn(p.bid, mul_rn(int_to_double((int)k), tick));          // :31
+                leg = sub_rn(sub_rn(p.mid_next, my_bid), mul_rn(my_bid, fee));                     // :46,:48
+            }
+        }
+    }
+    (side == 0 ? legs[t].leg_s : legs[t].leg_b)[j] = leg;
+}
+
+// leg tables of a bundle, one per fee rate seen (tick is a property of the bundle); built on first use on the caller's
+// stream, later users on other streams wait for the build through an event
+int tc32_legs(const sgmm_bundle* cb, double fee, cudaStream_t st, const tc32::BarLegs** out)
+{
+    using namespace tc32;
+    sgmm_bundle* b = const_cast<sgmm_bundle*>(cb);
+    *out = nullptr;
+    if (b->T == 0) return SGMM_OK;                                  // an empty episode visits no bar
+    std::lock_guard<std::mutex> lock(b->legs_mutex);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st) cudaStreamIsCapturing(st, &cap);
+    for (auto& e : b->legs) {
+        if (memcmp(&e.fee, &fee, sizeof fee) == 0) {
+            if (e.stream != st && cap == cudaStreamCaptureStatusNone)
+                if (int rc = check_cuda(cudaStreamWaitEvent(st, e.ready, 0), "cudaStreamWaitEvent(leg table)")) return rc;
+            *out = reinterpret_cast<const BarLegs*>(e.buf);
+            return SGMM_OK;
+        }
+    }
+    if (cap != cudaStreamCaptureStatusNone) {
+        set_error("the bundle has no leg table for fee_rate %g yet: run one tensor-core rollout with this fee outside the stream capture first", fee);
+        return SGMM_ERR_INVALID;
+    }
+    if (b->legs.size() >= 64) { set_error("more than 64 distinct fee rates on one bundle (each keeps a %zu-byte leg table)", (size_t)b->T * sizeof(BarLegs)); return SGMM_ERR_NOMEM; }
+    sgmm_bundle::LegTable e;
+    e.fee = fee; e.stream = st;
+    if (int rc = check_cuda(cudaMalloc(&e.buf, (size_t)b->T * sizeof(BarLegs)), "cudaMalloc(leg table)")) return rc;
+    if (int rc = check_cuda(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming), "cudaEventCreate(leg table)")) { cudaFree(e.buf); return rc; }
+    const int64_t n = b->T * 2 * LEG_N;
+    tc32_legs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b->T, b->sig, b->px, b->tick, fee, reinterpret_cast<BarLegs*>(e.buf));
+    int rc = check_cuda(cudaGetLastError(), "tc32_legs_kernel launch");
+    if (!rc) rc = check_cuda(cudaEventRecord(e.ready, st), "cudaEventRecord(leg table)");
+    if (rc) { cudaFree(e.buf); cudaEventDestroy(e.ready); return rc; }
+    b->legs.push_back(e);
+    *out = reinterpret_cast<const BarLegs*>(e.buf);
+    return SGMM_OK;
+}
+
 int launch_tc32(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, double phi, double fee, int group, double* fitness, int32_t* trades,
                 float* raw_table, int32_t* act_trace, cudaStream_t st, int mode)
 {
     using namespace tc32;
     if (mm.count == 0) return SGMM_OK;
     if (act_trace && !raw_table) { set_error("act_trace needs raw_table"); return SGMM_ERR_INVALID; }
-    if (adv) { set_error("the H=32 tensor-core rollout has no adversary path yet"); return SGMM_ERR_UNSUPPORTED; }
     Args a;
+    a.legs = nullptr;
+    if (adv) if (int rc = tc32_legs(b, fee, st, &a.legs)) return rc;     // only the adversary path accounts through the leg table
     a.sig = b->sig; a.px = b->px; a.a1 = b->a1 + (mode == M_F16 ? tc32_chunks(b->T) * A1_BYTES : 0); a.T = b->T; a.tick = b->tick; a.phi = phi; a.fee = fee;
     a.mm = mm; a.fitness = fitness; a.trades = trades; a.raw_table = raw_table; a.act_trace = act_trace;
+    if (adv) a.adv = *adv; else { PopArgs z = {}; a.adv = z; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
     a.group = (group >= 2 && group <= GMAX && group % 2 == 0) ? group : tc32_group_size(mm.count, sms);
     const int64_t groups = (mm.count + a.group - 1) / a.group;
     const int grid = (int)(groups < sms ? groups : sms);
     const size_t smem = sizeof(Smem) + 128;
-    static std::atomic<uint64_t> configured[6];       // per variant, one bit per device (zero-initialised)
-    const bool has_fee = fee != 0.0;
+    static std::atomic<uint64_t> configured[9];       // per variant, one bit per device (zero-initialised)
     if (mode < 0 || mode > 2) { set_error("unknown tensor-core mode %d", mode); return SGMM_ERR_INVALID; }
-    const int variant = (has_fee ? 1 : 0) + 2 * mode;
+    const int sub = adv ? 2 : (fee != 0.0 ? 1 : 0);            // plain, plain with fee, adversary
+    const int variant = sub + 3 * mode;
     void (*kern)(const Args) = nullptr;
     switch (variant) {
-        case 0: kern = tc32_kernel<false, M_BF16>; break;
-        case 1: kern = tc32_kernel<true, M_BF16>; break;
-        case 2: kern = tc32_kernel<false, M_TF32>; break;
-        case 3: kern = tc32_kernel<true, M_TF32>; break;
-        case 4: kern = tc32_kernel<false, M_F16>; break;
-        default: kern = tc32_kernel<true, M_F16>; break;
+        case 0: kern = tc32_kernel<false, false, M_BF16>; break;
+        case 1: kern = tc32_kernel<false, true, M_BF16>; break;
+        case 2: kern = tc32_kernel<true, false, M_BF16>; break;
+        case 3: kern = tc32_kernel<false, false, M_TF32>; break;
+        case 4: kern = tc32_kernel<false, true, M_TF32>; break;
+        case 5: kern = tc32_kernel<true, false, M_TF32>; break;
+        case 6: kern = tc32_kernel<false, false, M_F16>; break;
+        case 7: kern = tc32_kernel<false, true, M_F16>; break;
+        default: kern = tc32_kernel<true, false, M_F16>; break;
     }
     if (int rc = opt_in_smem(kern, smem, configured[variant], "cudaFuncSetAttribute(tc32 smem)")) return rc;
     kern<<<grid, NUM_THREADS, smem, st>>>(a);

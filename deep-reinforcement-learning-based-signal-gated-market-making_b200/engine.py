@@ -197,10 +197,14 @@ def rollout_seeded(bundle: Bundle, master, *, count, sigma, seed, generation, fi
     return fit, trd
 
 
-def rollout_tc_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0, hidden=32, group=0, precision="bf16"):
+TC_ADVERSARY = True          # the H=32 tensor-core rollout carries the adversary (sgmm_tc32.cu, 20-state automaton)
+
+
+def rollout_tc_audit(bundle: Bundle, genomes, adv_genomes=None, *, phi, fee_rate=0.0, hidden=32, group=0, precision="bf16"):
     """Tensor-core rollout (hidden=32: sgmm_tc32.cu, hidden=256: sgmm_spec256.cu) with its audit
     outputs: returns ``(fitness, trades, raw_table float32[P,T,5,2], act_trace int32[P,T,2])`` as
-    CUDA tensors -- the policy outputs for every (bar, inventory) and the offsets actually taken."""
+    CUDA tensors -- the policy outputs for every (bar, inventory) and the offsets actually taken (the market maker's,
+    before the adversary's displacement when ``adv_genomes`` is given; hidden=32 only)."""
     g = _as_f32_matrix(genomes, genome_len(hidden)).to(f"cuda:{bundle.device}")
     P, T = g.shape[0], bundle.T
     fit = torch.empty(P, dtype=torch.float64, device=g.device)
@@ -208,10 +212,16 @@ def rollout_tc_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0, hidden=32, g
     raw = torch.zeros(P, T, 5, 2, dtype=torch.float32, device=g.device)
     act = torch.zeros(P, T, 2, dtype=torch.int32, device=g.device)
     mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    advp = None
+    if adv_genomes is not None:
+        a = _as_adv_matrix(adv_genomes).to(g.device)
+        if a.shape[0] != P:
+            raise ValueError("adversary population size differs from the market-maker population")
+        adv = _lib.Population(32, 0, P, a.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+        advp = C.byref(adv)
     prm = _params(phi, fee_rate, units_per_lane=group, hidden=hidden, precision=precision)
-    _lib.check(_lib.lib().sgmm_rollout_spec256_audit(bundle.handle, C.byref(mm), C.byref(prm), fit.data_ptr(),
-                                                     trd.data_ptr(), raw.data_ptr(), act.data_ptr(),
-                                                     _stream(bundle.device)))
+    _lib.check(_lib.lib().sgmm_rollout_tc_audit(bundle.handle, C.byref(mm), advp, C.byref(prm), fit.data_ptr(),
+                                                trd.data_ptr(), raw.data_ptr(), act.data_ptr(), _stream(bundle.device)))
     return fit, trd, raw, act
 
 

@@ -42,6 +42,8 @@ extern "C" {
 
 /* precision of the policy MLP */
 #define SGMM_PRECISION_F32   0      /* SGMM-F32 order on CUDA cores: bit-identical to the oracle (H=32) */
+                                    /* The adversary (adv != NULL) runs on every H=32 path, tensor-core ones  */
+                                    /* included (a 20-state automaton instead of a 5-state one).              */
 #define SGMM_PRECISION_BF16  1      /* policy layers on tcgen05 tensor cores, bf16 x bf16 -> fp32 in  */
                                     /* TMEM, all 5 inventories of every bar evaluated at once:        */
                                     /*   H=32  all three layers as GEMMs chained through TMEM         */
@@ -135,7 +137,9 @@ typedef struct {
  *   - rollouts on one bundle must be ordered (one stream, or serialised): they share the scratch;
  *   - the first rollout of a given size allocates and therefore must not run under a stream capture (run one eagerly,
  *     then capture; a buffer that has been handed out is never freed before sgmm_bundle_destroy).
- * H = 32 rollouts (every precision) are one kernel with no scratch. */
+ * H = 32 rollouts are one kernel with no per-rollout scratch.  The tensor-core precisions read a per-(bundle, fee_rate)
+ * table of the reference's exact fp64 P&L legs (272 B per bar), built on the first rollout with that fee rate: that
+ * first rollout must not run under a stream capture either. */
 int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm,
                             const sgmm_population* adv, const sgmm_rollout_params* params,
                             double* fitness, int32_t* trades, void* stream);
@@ -165,6 +169,12 @@ int sgmm_rollout_wait(const sgmm_bundle* bundle, int32_t ticket);
 int sgmm_rollout_spec256_audit(const sgmm_bundle* bundle, const sgmm_population* mm,
                                const sgmm_rollout_params* params, double* fitness, int32_t* trades,
                                float* raw_table, int32_t* act_trace, void* stream);
+/* The same with an adversary population (hidden = 32 only; adv may be NULL): act_trace holds the market maker's offsets
+ * BEFORE the adversary's displacement (the recorder's off_a / off_b, Env/recorder.py:12), so that replaying them through
+ * the reference's env together with the adversary genome reproduces the episode. */
+int sgmm_rollout_tc_audit(const sgmm_bundle* bundle, const sgmm_population* mm, const sgmm_population* adv,
+                          const sgmm_rollout_params* params, double* fitness, int32_t* trades,
+                          float* raw_table, int32_t* act_trace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-step trace of ONE individual: the recorder row contract (Env/recorder.py:8-36,

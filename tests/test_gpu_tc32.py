@@ -181,7 +181,7 @@ def test_device_ga_with_tensor_core_population(sg, orc):
     """sgmm_ga_config.precision = BF16: the population is evaluated by the tensor-core rollout, the
     argmax / tell / master update are unchanged, and the validation rollout of the best child is the
     exact fp32 kernel (bit-identical to the oracle)."""
-    from sgmm_b200 import synthetic, SgmmError
+    from sgmm_b200 import synthetic
     from sgmm_b200.engine import DeviceGA
     bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 95, 1, seed=4)
     vb = synthetic.synthetic_bundle(1, first_day=96)
@@ -205,6 +205,100 @@ def test_device_ga_with_tensor_core_population(sg, orc):
     assert np.array_equal(mm, child)
     fo, to = orc.rollout(child, None, (vz1, vz2) + vb[2:], 1e-4, 0.001, 0.0)
     assert h["val_f"][0] == fo and h["val_trades"][0] == to
-    with pytest.raises(SgmmError):
-        DeviceGA(master, np.zeros(1250, np.float32), pop_size=8, sigma=0.05, phi=1e-4, fee_rate=0.0, use_arl=True,
-                 seed=1, max_generations=2, precision="bf16")
+    # adversarial co-training on the tensor-core path: both masters follow the composed rollout's argmax / argmin
+    adv_master = (np.random.default_rng(6).standard_normal(1250) * 0.5).astype(np.float32)
+    ga = DeviceGA(master, adv_master, pop_size=50, sigma=0.05, phi=1e-4, fee_rate=0.0, use_arl=True, seed=13,
+                  max_generations=2, precision="f16")
+    try:
+        ga.generation(bun, val)
+        h = ga.history(1)
+        mm, adv, best = ga.masters()
+    finally:
+        ga.close()
+    f, t = sg.rollout_seeded(bun, torch.from_numpy(master).cuda(), count=50, sigma=0.05, seed=13, generation=0,
+                             adv_master=torch.from_numpy(adv_master).cuda(), phi=1e-4, precision="f16")
+    f, t = f.cpu().numpy(), t.cpu().numpy()
+    i, ia = int(np.argmax(f)), int(np.argmax(-f))
+    assert h["train_f"][0] == f[i] and h["train_trades"][0] == t[i]
+    assert np.array_equal(mm, orc.mutate(master, 0.05, 13, 0, i))
+    assert np.array_equal(adv, orc.mutate(adv_master, 0.05, 13 ^ 0x8000000000000000, 0, ia))
+
+
+# ----------------------------------------------------------------------------------------------
+# the adversary on the tensor-core path (BASELINE config 3): a 20-state automaton in the walker
+# ----------------------------------------------------------------------------------------------
+def _adv_genomes(P, seed, scale=0.7):
+    return (np.random.default_rng(seed).standard_normal((P, 1250)) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "f16"])
+@pytest.mark.parametrize("fee", [0.0, 3e-4])
+def test_adversary_env_bit_exact_given_offsets(sg, orc, fee, precision):
+    """With the adversary: GIVEN the market maker's offsets the kernel took, the displacement (the oracle's own
+    adv_forward on [inv/2, fill_sell_prev, fill_buy_prev]), fills, inventory, trades, rewards and fitness are
+    bit-identical to the oracle's (teacher-forced replay WITH the adversary genome); policy outputs within tolerance."""
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 97, 6, seed=21)
+    adv = _adv_genomes(6, 22)
+    T = bun.T
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, adv, phi=1e-4, fee_rate=fee, hidden=32, precision=precision)
+    f2, t2 = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), torch.from_numpy(adv).cuda(), phi=1e-4, fee_rate=fee,
+                                   precision=precision)
+    assert torch.equal(f2, fit) and torch.equal(t2, trd)
+    fit, trd, raw, act = fit.cpu().numpy(), trd.cpu().numpy(), raw.cpu().numpy(), act.cpu().numpy()
+    displaced = 0
+    for i in range(genomes.shape[0]):
+        fo, to, tro = orc.rollout(None, adv[i], bz, 1e-4, 0.001, fee, forced_actions=act[i], trace=True)
+        assert fo == fit[i] and to == trd[i], (i, fo, fit[i], to, trd[i])
+        inv_before = np.concatenate([[0], tro["inventory"][:-1]])
+        taken = np.rint(raw[i, np.arange(T), inv_before + 2] * np.float32(5.0)).astype(np.int32)
+        assert np.array_equal(taken, act[i])
+        displaced += int(np.sum((tro["adv_a"] != 0) | (tro["adv_b"] != 0)))
+    assert displaced > 0, "the adversaries of this case should displace some quotes"
+    worst, flips_outside = _audit(orc, bz, genomes[:2], raw[:2], T, TAU[precision])
+    assert worst <= TAU[precision] and flips_outside == 0
+    # the adversary matters
+    f0, _ = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, fee_rate=fee, precision=precision)
+    assert not np.array_equal(f0.cpu().numpy(), fit)
+
+
+@pytest.mark.parametrize("T,P,group", [(1, 3, 0), (25, 150, 0), (26, 17, 16), (51, 33, 6), (240, 300, 0)])
+def test_adversary_ragged_lengths_and_groups(sg, orc, T, P, group):
+    precision = "f16" if (T % 2) else "tf32"
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 98, P, seed=T, T=T)
+    adv = _adv_genomes(P, 100 + T)
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, adv, phi=1e-4, hidden=32, group=group, precision=precision)
+    fit, trd, act = fit.cpu().numpy(), trd.cpu().numpy(), act.cpu().numpy()
+    for i in list(range(0, P, max(1, P // 9))) + [P - 1]:
+        fo, to = orc.rollout(None, adv[i], bz, 1e-4, 0.001, 0.0, forced_actions=act[i])
+        assert fo == fit[i] and to == trd[i], (i, fo, fit[i])
+
+
+def test_adversary_seeded_children_and_74_float_genomes(sg, orc):
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 99, 1, seed=3, T=120)
+    adv_master = _adv_genomes(1, 7)[0]
+    kids = np.stack([orc.mutate(master, 0.05, 77, 4, 10 + i) for i in range(9)])
+    akids = np.stack([orc.mutate(adv_master, 0.05, 77 ^ 0x8000000000000000, 4, 10 + i) for i in range(9)])
+    f_exp, t_exp = sg.rollout_population(bun, torch.from_numpy(kids).cuda(), torch.from_numpy(akids).cuda(), phi=1e-4, precision="f16")
+    f_seed, t_seed = sg.rollout_seeded(bun, torch.from_numpy(master).cuda(), count=9, sigma=0.05, seed=77, generation=4, first_index=10,
+                                       adv_master=torch.from_numpy(adv_master).cuda(), phi=1e-4, precision="f16")
+    assert torch.equal(f_exp, f_seed) and torch.equal(t_exp, t_seed)
+    # a native 74-float AdversaryPolicy genome (models/model.py:52-57 reads only the first 74 floats)
+    f74, t74 = sg.rollout_population(bun, torch.from_numpy(kids).cuda(), torch.from_numpy(akids[:, :74].copy()).cuda(), phi=1e-4, precision="f16")
+    assert torch.equal(f74, f_exp) and torch.equal(t74, t_exp)
+    fx, tx = sg.rollout_population(bun, torch.from_numpy(kids).cuda(), torch.from_numpy(akids[:, :74].copy()).cuda(), phi=1e-4)     # exact path
+    fy, ty = sg.rollout_population(bun, torch.from_numpy(kids).cuda(), torch.from_numpy(akids).cuda(), phi=1e-4)
+    assert torch.equal(fx, fy) and torch.equal(tx, ty)
+
+
+@pytest.mark.parametrize("out_scale,fee,use_adv", [(300.0, 0.0, False), (40000.0, 3e-4, True), (4e9, 3e-5, True)])
+def test_offsets_outside_the_leg_table_take_the_literal_path(sg, orc, out_scale, fee, use_adv):
+    """Offsets of hundreds to billions of ticks (both signs, clamped to +-2^30 before the displacement): fills far inside
+    the threshold fall outside the 16-entry leg table of the bar and are accounted by the literal fp64 expression."""
+    bundle, bz, bun, master, genomes = _setup(sg, orc, 1, 93, 9, seed=3, T=333, out_scale=out_scale)
+    adv = _adv_genomes(9, 5) if use_adv else None
+    fit, trd, raw, act = sg.rollout_tc_audit(bun, genomes, adv, phi=1e-4, fee_rate=fee, hidden=32, precision="tf32")
+    fit, trd, act = fit.cpu().numpy(), trd.cpu().numpy(), act.cpu().numpy()
+    assert np.abs(act).max() > 50 * min(out_scale, 1e6) / 300.0
+    for i in range(genomes.shape[0]):
+        fo, to = orc.rollout(None, adv[i] if use_adv else None, bz, 1e-4, 0.001, fee, forced_actions=act[i])
+        assert fo == fit[i] and to == trd[i], (i, fo, fit[i], to, trd[i])
