@@ -45,7 +45,8 @@ class RolloutParams(C.Structure):
 class Trace(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("off_a", "off_b", "adv_a", "adv_b", "fill_buy", "fill_sell", "inventory",
-                 "cash", "reward", "pnl_reward", "inventory_reward", "fee_paid", "raw_a", "raw_b")]
+                 "cash", "reward", "pnl_reward", "inventory_reward", "fee_paid", "raw_a", "raw_b",
+                 "spread", "wealth", "cum_reward", "skew", "cum_fees", "unrealized_pnl")]
 
 
 class EnvState(C.Structure):

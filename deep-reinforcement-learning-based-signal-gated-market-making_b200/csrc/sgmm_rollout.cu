@@ -582,6 +582,7 @@ __global__ void __launch_bounds__(32, 1) trace_kernel_h32(const TraceArgs a)
     env.phi = a.phi; env.tick_size = a.tick; env.fee_rate = a.fee;
     env.inventory = 0; env.cash = 0.0; env.i_max = 2; env.i_min = -2;         // market_env.py:9-15
     double total = 0.0; int trades = 0; int fbp = 0, fsp = 0;
+    double cum_fees = 0.0;                                                     // Env/recorder.py:49
     for (int64_t t = 0; t < a.T; ++t) {
         const BarSig sg = a.sig[t];
         const BarPx px = a.px[t];
@@ -640,6 +641,15 @@ __global__ void __launch_bounds__(32, 1) trace_kernel_h32(const TraceArgs a)
             if (tr.fee_paid) tr.fee_paid[t] = info.fee_paid;
             if (tr.raw_a) tr.raw_a[t] = ra;
             if (tr.raw_b) tr.raw_b[t] = rb;
+            // derived columns (Env/recorder.py:45-51); `mid` of a recorded row is the bar's mid_next (agent_trainer.py:153)
+            cum_fees = add_rn(cum_fees, info.fee_paid);
+            const double unreal = mul_rn((double)env.inventory, px.mid_next);
+            if (tr.spread) tr.spread[t] = sub_rn(px.ask, px.bid);
+            if (tr.wealth) tr.wealth[t] = add_rn(env.cash, unreal);
+            if (tr.cum_reward) tr.cum_reward[t] = total;
+            if (tr.skew) tr.skew[t] = kb - ka;
+            if (tr.cum_fees) tr.cum_fees[t] = cum_fees;
+            if (tr.unrealized_pnl) tr.unrealized_pnl[t] = unreal;
         }
     }
     if (trades == 0) total = sub_rn(total, 50.0);

@@ -229,8 +229,9 @@ def rollout_spec256_audit(bundle: Bundle, genomes, *, phi, fee_rate=0.0):
     return rollout_tc_audit(bundle, genomes, phi=phi, fee_rate=fee_rate, hidden=256)
 
 
-_TRACE_I32 = ("off_a", "off_b", "adv_a", "adv_b", "fill_buy", "fill_sell", "inventory")
-_TRACE_F64 = ("cash", "reward", "pnl_reward", "inventory_reward", "fee_paid")
+_TRACE_I32 = ("off_a", "off_b", "adv_a", "adv_b", "fill_buy", "fill_sell", "inventory", "skew")
+_TRACE_F64 = ("cash", "reward", "pnl_reward", "inventory_reward", "fee_paid",
+              "spread", "wealth", "cum_reward", "cum_fees", "unrealized_pnl")      # the last five: Env/recorder.py:45-51, on the device
 _TRACE_F32 = ("raw_a", "raw_b")
 
 

@@ -43,6 +43,10 @@ class StrategyRecorder:
             'pnl_reward': trace['pnl_reward'], 'inventory_reward': trace['inventory_reward'],
             'fill_buy': trace['fill_buy'].astype(np.int64), 'fill_sell': trace['fill_sell'].astype(np.int64),
         }
+        # the derived columns of recorder.py:45-51 come from the same kernel pass (sequential fp64 running sums in bar
+        # order == pandas cumsum); to_dataframe only attaches them
+        rec._derived = {k: (trace[k].astype(np.int64) if k == 'skew' else trace[k])
+                        for k in ('spread', 'wealth', 'cum_reward', 'skew', 'cum_fees', 'unrealized_pnl') if k in trace}
         return rec
 
     def to_dataframe(self):
@@ -58,7 +62,13 @@ class StrategyRecorder:
             if 'ask' not in df.columns and 'best_ask' in df.columns:
                 df['ask'] = df['best_ask']
                 df['bid'] = df['best_bid']
-        # derived columns (recorder.py:45-51)
+        d = getattr(self, "_derived", None)
+        if d is not None and len(d) == 6:          # device trace: derived columns already computed by the kernel
+            df['spread'] = d['spread']; df['wealth'] = d['wealth']; df['cum_reward'] = d['cum_reward']
+            df['skew'] = d['skew']; df['cum_fees'] = d['cum_fees']; df['realized_pnl'] = df['cash']
+            df['unrealized_pnl'] = d['unrealized_pnl']
+            return df
+        # derived columns (recorder.py:45-51) for rows recorded one by one on the host
         df['spread'] = df['ask'] - df['bid']
         df['wealth'] = df['cash'] + df['inventory'] * df['mid']
         df['cum_reward'] = df['reward'].cumsum()

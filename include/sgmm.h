@@ -189,6 +189,14 @@ typedef struct {
     int32_t* inventory;                  /* post-step                                            */
     double* cash; double* reward; double* pnl_reward; double* inventory_reward; double* fee_paid;
     float* raw_a; float* raw_b;          /* policy outputs before x5 and rounding                */
+    /* the recorder's DERIVED columns (Env/recorder.py:45-51), computed in the same kernel pass: the two running sums
+     * are sequential fp64 sums in bar order, exactly what pandas' cumsum does */
+    double* spread;                      /* ask - bid                                            */
+    double* wealth;                      /* cash + inventory * mid                               */
+    double* cum_reward;                  /* reward.cumsum()                                      */
+    int32_t* skew;                       /* off_b - off_a                                        */
+    double* cum_fees;                    /* fee_paid.cumsum()                                    */
+    double* unrealized_pnl;              /* inventory * mid     (realized_pnl is the cash column) */
 } sgmm_trace;
 
 int sgmm_rollout_trace(const sgmm_bundle* bundle, const float* mm_genome, int32_t hidden,

@@ -108,8 +108,12 @@ def test_device_replay_of_golden_backtests_bit_exact(sg, golden, name):
     assert fit == np.cumsum(b[f"{name}.reward"])[-1]
     df = sg.StrategyRecorder.from_trace(tr, (b[f"{name}.s1_pred"], b[f"{name}.s2_pred"], b[f"{name}.mid"],
                                              b[f"{name}.ask"], b[f"{name}.bid"], None, None)).to_dataframe()
-    for c in ("wealth", "cum_reward", "spread", "skew"):
+    # the derived columns come from the kernel (running fp64 sums in bar order) and equal the reference's pandas columns bit for bit
+    for c in ("wealth", "cum_reward", "spread", "skew", "cum_fees", "realized_pnl", "unrealized_pnl"):
         assert np.array_equal(df[c].to_numpy(), b[f"{name}.{c}"]), c
+        if c in tr:
+            assert np.array_equal(np.asarray(tr[c], df[c].to_numpy().dtype), b[f"{name}.{c}"]), c
+    assert all(k in tr for k in ("spread", "wealth", "cum_reward", "skew", "cum_fees", "unrealized_pnl"))
 
 
 def test_device_policy_reproduces_arl_checkpoint_actions(sg, golden):

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Population) == 64
     assert C.sizeof(_lib.RolloutParams) == 32
-    assert C.sizeof(_lib.Trace) == 14 * 8
+    assert C.sizeof(_lib.Trace) == 20 * 8
     assert C.sizeof(_lib.EnvState) == 56 and C.sizeof(_lib.StepInfo) == 40
     assert C.sizeof(_lib.GaConfig) == 80 and C.sizeof(_lib.GaStatus) == 32
     L = _lib.lib()

@@ -14,7 +14,9 @@ keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__average_warp_latency_per_inst_issued.ratio", "sm__cycles_elapsed.avg.per_second",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
 for h, u, v in zip(hdr, units, vals):
     if h in keys:
         print(f"{h:75s} {v} {u}")
