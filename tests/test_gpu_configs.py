@@ -345,3 +345,45 @@ def test_second_device_in_process_if_present(sg):
             f16, _ = sg.rollout_population(bun, torch.from_numpy(genomes).to(f"cuda:{d}"), phi=1e-4, precision="f16")
         res.append((f.cpu(), t.cpu(), f16.cpu()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
+# ----------------------------------------------------------------------------------------------
+# memory safety without compute-sanitizer (closed on this pool): canaries around every output buffer
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden,precision,use_adv,P,T", [(32, "f32", True, 29, 131), (32, "f32", False, 3, 1), (32, "f16", False, 17, 51),
+                                                           (32, "tf32", True, 9, 26), (32, "bf16", True, 150, 25), (256, "bf16", False, 5, 27)])
+def test_kernels_write_nothing_outside_their_output_buffers(sg, hidden, precision, use_adv, P, T):
+    import ctypes as C
+    from sgmm_b200 import _lib, synthetic
+    from sgmm_b200.engine import _params
+    bundle = tuple(a[:T] for a in synthetic.synthetic_bundle(1, first_day=180))
+    stats = synthetic.train_stats_of(synthetic.synthetic_bundle(1, first_day=180))
+    bun = sg.Bundle.from_arrays(bundle, stats, 0.001)
+    _, genomes = synthetic.policy_like_genomes(P, hidden=hidden, seed=P, out_scale=4.0)
+    g = torch.from_numpy(genomes).cuda()
+    adv = torch.from_numpy((np.random.default_rng(1).standard_normal((P, 1250)) * 0.5).astype(np.float32)).cuda() if use_adv else None
+    PAD = 64
+    CAN_F, CAN_I = -1.2345e300, -77777777
+    fit = torch.full((P + 2 * PAD,), CAN_F, dtype=torch.float64, device="cuda")
+    trd = torch.full((P + 2 * PAD,), CAN_I, dtype=torch.int32, device="cuda")
+    audit = precision != "f32"
+    raw = torch.full((P * T * 10 + 2 * PAD,), 7.25, dtype=torch.float32, device="cuda") if audit else None
+    act = torch.full((P * T * 2 + 2 * PAD,), CAN_I, dtype=torch.int32, device="cuda") if audit else None
+    mm = _lib.Population(hidden, 0, P, g.data_ptr(), None, 0.0, 0.0, 0, 0, 0)
+    ad = _lib.Population(32, 0, P, adv.data_ptr(), None, 0.0, 0.0, 0, 0, 0) if use_adv else None
+    prm = _params(1e-4, 3e-5, hidden=hidden, precision=precision)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L = _lib.lib()
+    if audit:
+        _lib.check(L.sgmm_rollout_tc_audit(bun.handle, C.byref(mm), None if ad is None else C.byref(ad), C.byref(prm),
+                                           fit.data_ptr() + PAD * 8, trd.data_ptr() + PAD * 4, raw.data_ptr() + PAD * 4,
+                                           act.data_ptr() + PAD * 4, st))
+    else:
+        _lib.check(L.sgmm_rollout_population(bun.handle, C.byref(mm), None if ad is None else C.byref(ad), C.byref(prm),
+                                             fit.data_ptr() + PAD * 8, trd.data_ptr() + PAD * 4, st))
+    torch.cuda.synchronize()
+    for buf, can, n in ((fit, CAN_F, P), (trd, CAN_I, P)) + (((raw, 7.25, P * T * 10), (act, CAN_I, P * T * 2)) if audit else ()):
+        assert bool((buf[:PAD] == can).all()) and bool((buf[PAD + n:] == can).all()), "a kernel wrote outside its output buffer"
+    assert bool((fit[PAD:PAD + P] != CAN_F).all()) and bool((trd[PAD:PAD + P] != CAN_I).all())
+    if audit:
+        assert bool((act[PAD:PAD + P * T * 2] != CAN_I).all())
