@@ -1,0 +1,204 @@
+// sgmm_one.cu -- ONE individual's episode, fast: the validation rollout of a GA generation (Env/drl_engine.py:129-140:
+// the generation's best child on the validation bundle, adversary off) and any other single-policy episode.
+//
+// The population kernel gives an individual one warp (or eight lanes) and walks the bars one after the other: for a
+// single individual that is one latency-bound warp on one SM (2 880 bars = 0.64 ms, 13 % of a 4096-individual
+// generation; at the reference's own scale -- population 50, one day -- as long as the population rollout itself).
+// With no adversary the action at bar t depends on (t, inventory) only and the inventory has five values
+// (SURVEY.md 7.3), so the episode splits into
+//   1. policy_table_kernel  the exact policy (SGMM-F32 order, identical instruction sequence to trace_kernel_h32) for
+//                           EVERY (bar, inventory) pair -- 5 T independent evaluations spread over the whole GPU -- and
+//                           the integer half of the env step of the pair: fills, next inventory, 8-byte step code;
+//   2. walk_account_kernel  one CTA: the walk through the 5-state automaton as a parallel prefix scan over function
+//                           composition (every bar is a map {0..4} -> {0..4}; composition is associative), then the fp64
+//                           half for the visited pairs in parallel, and the one thing that is inherently serial -- the
+//                           reference-order fp64 reward sum (drl_engine.py:54) -- by one thread, chunk by chunk.
+// 5x the policy FLOPs of the sequential walk, ~10x less time; results bit-identical to rollout_kernel_h32 (the GA
+// parity tests compare the whole history with the oracle's).
+#include "sgmm_internal.h"
+#include "sgmm_rng.cuh"
+#include "sgmm_step_core.h"
+
+namespace sgmm {
+
+namespace one {
+
+constexpr int H = 32;
+constexpr int WALK_THREADS = 1024;
+constexpr int SUM_CHUNK = 2048;            // bars whose rewards sit in shared memory while one thread sums them
+
+struct Scratch {                           // per (bar, inventory index) pair, written by policy_table_kernel
+    float2* code;                          // [T][5]  q = raw*5 of each side that filled, NaN marker otherwise
+    uint8_t* next;                         // [T][8]  next inventory index (bytes 0..4)
+};
+
+__global__ void __launch_bounds__(128) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const float* __restrict__ genome,
+                                                            float2* __restrict__ code, uint8_t* __restrict__ next)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // weights of hidden unit `lane` (models/model.py:31-36 layout), exactly as trace_kernel_h32 holds them
+    const int j = lane;
+    const float w1x = __ldg(genome + 3 * j), w1y = __ldg(genome + 3 * j + 1), w1i = __ldg(genome + 3 * j + 2);
+    const float b1 = __ldg(genome + 3 * H + j), b2 = __ldg(genome + 4 * H + H * H + j);
+    const float w3a = __ldg(genome + 5 * H + H * H + j), w3b = __ldg(genome + 6 * H + H * H + j);
+    const float b3a = __ldg(genome + 7 * H + H * H), b3b = __ldg(genome + 7 * H + H * H + 1);
+    float w2[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) w2[k] = __ldg(genome + 4 * H + j * H + k);
+    for (int64_t p = warp; p < T * 5; p += nwarps) {
+        const int64_t t = p / 5;
+        const int iv = (int)(p - t * 5);
+        const float4 sg = *reinterpret_cast<const float4*>(&sig[t]);              // z1, z2, tha, thb
+        const float inv2 = (float)(iv - 2) * 0.5f;                                 // drl_engine.py:35
+        // ---- TradingPolicy.forward in SGMM-F32 order (models/model.py:9-15) ----
+        float v = __fmaf_rn(w1x, sg.x, b1);
+        v = __fmaf_rn(w1y, sg.y, v);
+        v = __fmaf_rn(w1i, inv2, v);
+        const float h1 = fmaxf(v, 0.0f);
+        float c0 = b2, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+            c0 = __fmaf_rn(w2[k + 0], __shfl_sync(0xffffffffu, h1, k + 0), c0);
+            c1 = __fmaf_rn(w2[k + 1], __shfl_sync(0xffffffffu, h1, k + 1), c1);
+            c2 = __fmaf_rn(w2[k + 2], __shfl_sync(0xffffffffu, h1, k + 2), c2);
+            c3 = __fmaf_rn(w2[k + 3], __shfl_sync(0xffffffffu, h1, k + 3), c3);
+        }
+        const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)), 0.0f);
+        float ra = __fmul_rn(w3a, h2), rb = __fmul_rn(w3b, h2);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            ra = __fadd_rn(ra, __shfl_xor_sync(0xffffffffu, ra, m));
+            rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
+        }
+        const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);                      // raw*5.0 (drl_engine.py:39)
+        const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
+        // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
+        const bool fb = (inv2 < 1.0f) && (qb < sg.w);                              // market_env.py:34,37
+        const bool fs = (inv2 > -1.0f) && (qa < sg.z);                             // :35,:38
+        if (lane == 0) {
+            code[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
+            next[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));        // :45,:51
+        }
+    }
+}
+
+// maps {0..4} -> {0..4} packed 3 bits per entry
+__device__ __forceinline__ uint32_t map_of(const uint8_t* n) { return n[0] | (n[1] << 3) | (n[2] << 6) | (n[3] << 9) | (n[4] << 12); }
+__device__ __forceinline__ uint32_t map_at(uint32_t m, uint32_t e) { return (m >> (3u * e)) & 7u; }
+// (g after f)[e] = g[f[e]]
+__device__ __forceinline__ uint32_t map_then(uint32_t f, uint32_t g)
+{
+    return map_at(g, map_at(f, 0)) | (map_at(g, map_at(f, 1)) << 3) | (map_at(g, map_at(f, 2)) << 6) | (map_at(g, map_at(f, 3)) << 9) |
+           (map_at(g, map_at(f, 4)) << 12);
+}
+constexpr uint32_t MAP_ID = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
+
+__global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_kernel(const BarPx* __restrict__ px, int64_t T, const float2* __restrict__ code,
+                                                                         const uint8_t* __restrict__ next, double tick, double phi, double fee,
+                                                                         double* __restrict__ fitness, int32_t* __restrict__ trades)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ int s_trades;
+    __shared__ double s_rew[SUM_CHUNK];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_trades = 0;
+    // ---- 1. every thread composes the maps of its contiguous segment of bars ----
+    const int64_t L = (T + WALK_THREADS - 1) / WALK_THREADS;
+    const int64_t t_lo = (int64_t)tid * L < T ? (int64_t)tid * L : T, t_hi = t_lo + L < T ? t_lo + L : T;
+    uint32_t m = MAP_ID;
+    for (int64_t t = t_lo; t < t_hi; ++t) m = map_then(m, map_of(next + t * 8));
+    // ---- 2. exclusive scan over the segments (composition is associative, not commutative: earlier bars first) ----
+    uint32_t inc = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = map_then(o, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w = map_then(o, w);
+        }
+        s_warp[lane] = w;                                   // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);   // everything before this thread inside its warp
+    if (lane == 0) before = MAP_ID;
+    if (warp > 0) before = map_then(s_warp[warp - 1], before);
+    uint32_t iv = map_at(before, 2);                        // the episode starts flat: inventory 0 = index 2 (market_env.py:17)
+    // ---- 3. the fp64 half for the visited pairs, chunk by chunk; one thread sums each chunk in bar order ----
+    const double pen0 = mul_rn(phi, 0.0), pen1 = mul_rn(phi, 1.0), pen2 = mul_rn(phi, 2.0);       // market_env.py:57
+    int ntr = 0;
+    double total = 0.0;                                     // thread 0 only (drl_engine.py:26)
+    for (int64_t c0 = 0; c0 < T; c0 += SUM_CHUNK) {
+        const int64_t c1 = c0 + SUM_CHUNK < T ? c0 + SUM_CHUNK : T;
+        const int64_t a = t_lo > c0 ? t_lo : c0, b = t_hi < c1 ? t_hi : c1;       // this thread's bars inside the chunk
+        for (int64_t t = a; t < b; ++t) {
+            const float2 q = code[t * 5 + iv];
+            int ka = __float_as_int(q.x), kb = __float_as_int(q.y);
+            const bool fs = ka != SGMM_CODE_NOFILL_F, fb = kb != SGMM_CODE_NOFILL_F;
+            const uint32_t niv = next[t * 8 + iv];
+            ntr += (fb || fs) ? 1 : 0;                                             // drl_engine.py:60-61
+            double pnl = 0.0;                                                      // market_env.py:40
+            if (fb || fs) {
+                const BarPx p = px[t];
+                ka = __float2int_rn(q.x); kb = __float2int_rn(q.y);                // drl_engine.py:39
+                const double my_ask = add_rn(p.ask, mul_rn((double)ka, tick));     // market_env.py:30
+                const double my_bid = sub_rn(p.bid, mul_rn((double)kb, tick));     // :31
+                double leg_b = sub_rn(p.mid_next, my_bid), leg_s = sub_rn(my_ask, p.mid_next);
+                leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                        // :46,:48 (fee terms evaluated as the reference does, fee_rate 0 included)
+                leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                        // :52,:54
+                pnl = fb ? add_rn(pnl, leg_b) : pnl;
+                pnl = fs ? add_rn(pnl, leg_s) : pnl;
+            }
+            const int ai = niv < 2u ? 2 - (int)niv : (int)niv - 2;
+            s_rew[t - c0] = sub_rn(pnl, ai == 0 ? pen0 : (ai == 1 ? pen1 : pen2));                 // :57-58
+            iv = niv;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int n = (int)(c1 - c0);
+            for (int i = 0; i < n; ++i) total = add_rn(total, s_rew[i]);           // drl_engine.py:54
+        }
+        __syncthreads();
+    }
+    if (ntr) atomicAdd(&s_trades, ntr);
+    __syncthreads();
+    if (tid == 0) {
+        const int n = s_trades;
+        if (n == 0) total = sub_rn(total, 50.0);                                   // drl_engine.py:64-65
+        *fitness = total; *trades = n;
+    }
+}
+
+}  // namespace one
+
+size_t rollout_one_scratch_bytes(int64_t T) { return (size_t)T * (5 * sizeof(float2) + 8) + 256; }
+
+// One individual's episode on `b` (explicit genome, H = 32, no adversary) through the two kernels above.  `scratch`:
+// rollout_one_scratch_bytes(b->T) bytes of device memory owned by the caller.
+int launch_rollout_one(const sgmm_bundle* b, const float* genome, double phi, double fee, void* scratch, double* fitness,
+                       int32_t* trades, cudaStream_t st)
+{
+    using namespace one;
+    const int64_t T = b->T;
+    float2* code = reinterpret_cast<float2*>(scratch);
+    uint8_t* next = reinterpret_cast<uint8_t*>(code + (T * 5 + 15) / 16 * 16);
+    if (T > 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+        const int64_t pairs = T * 5, warps_wanted = (pairs + 3) / 4;               // ~4 pairs per warp: latency, not throughput
+        const int64_t blocks = (warps_wanted + 3) / 4 < (int64_t)sms * 8 ? (warps_wanted + 3) / 4 : (int64_t)sms * 8;
+        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 128, 0, st>>>(b->sig, T, genome, code, next);
+        if (int rc = check_cuda(cudaGetLastError(), "policy_table_kernel launch")) return rc;
+    }
+    walk_account_kernel<<<1, WALK_THREADS, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
+    return check_cuda(cudaGetLastError(), "walk_account_kernel launch");
+}
+
+}  // namespace sgmm

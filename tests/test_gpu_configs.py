@@ -387,3 +387,33 @@ def test_kernels_write_nothing_outside_their_output_buffers(sg, hidden, precisio
     assert bool((fit[PAD:PAD + P] != CAN_F).all()) and bool((trd[PAD:PAD + P] != CAN_I).all())
     if audit:
         assert bool((act[PAD:PAD + P * T * 2] != CAN_I).all())
+
+
+# ----------------------------------------------------------------------------------------------
+# the GA's validation rollout: policy table for every (bar, inventory) + automaton scan + reference-order sum
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("days,T", [(1, 0), (1, 1), (1, 7), (1, 240), (9, 2049), (12, 2880), (250, 60000)])
+@pytest.mark.parametrize("fee", [0.0, 3e-4])
+def test_validation_fast_path_is_bit_identical_to_the_sequential_kernel_and_the_oracle(sg, orc, days, T, fee):
+    """sgmm_one.cu (one individual's episode as 5T parallel policy evaluations + a prefix scan over the 5-state automaton)
+    against rollout_kernel_h32 and the oracle: empty, single-bar, ragged, chunk-boundary (2048 + 1) and 60 000-bar episodes."""
+    from sgmm_b200 import synthetic
+    from sgmm_b200.engine import DeviceGA
+    vb = tuple(a[:T] for a in synthetic.synthetic_bundle(days, first_day=400))
+    tb = synthetic.synthetic_bundle(1, first_day=399)
+    stats = synthetic.train_stats_of(tb)
+    train, val = sg.Bundle.from_arrays(tb, stats, 0.001), sg.Bundle.from_arrays(vb, stats, 0.001)
+    master, _ = synthetic.policy_like_genomes(1, seed=T + 1, out_scale=4.0, out_bias=(0.1, 0.1))
+    ga = DeviceGA(master, None, pop_size=6, sigma=0.05, phi=1e-4, fee_rate=fee, use_arl=False, seed=3, max_generations=3)
+    ga.generation(train, val)
+    ga.generation(train, val)
+    h = ga.history(2)
+    mm, _, _ = ga.masters()
+    ga.close()
+    f, t = sg.rollout_population(val, torch.from_numpy(mm[None]).cuda(), phi=1e-4, fee_rate=fee)        # the sequential kernel
+    z1, z2 = orc.normalise(vb, stats)
+    fo, to = orc.rollout(mm, None, (z1, z2) + vb[2:], 1e-4, 0.001, fee)
+    assert h["val_f"][1] == f.item() == fo, (h["val_f"][1], f.item(), fo)
+    assert h["val_trades"][1] == t.item() == to
+    if T >= 240:
+        assert to > 0
