@@ -148,7 +148,6 @@ struct sgmm_ga {
     GaDev* st = nullptr;
     double* h_train_f = nullptr; double* h_val_f = nullptr; int32_t* h_train_t = nullptr; int32_t* h_val_t = nullptr;
     float* h_sigma = nullptr;
-    void* val_scratch = nullptr; size_t val_scratch_bytes = 0;      // policy table of the validation rollout (sgmm_one.cu), grow-only
 };
 
 namespace {
@@ -232,7 +231,7 @@ int sgmm_ga_destroy(sgmm_ga* ga)
         cudaFree(ga->mm_master); cudaFree(ga->adv_master); cudaFree(ga->best_master);
         cudaFree(ga->gather.base); cudaFree(ga->val_fit); cudaFree(ga->val_trd);
         cudaFree(ga->st); cudaFree(ga->h_train_f); cudaFree(ga->h_val_f); cudaFree(ga->h_train_t);
-        cudaFree(ga->h_val_t); cudaFree(ga->h_sigma); cudaFree(ga->val_scratch);
+        cudaFree(ga->h_val_t); cudaFree(ga->h_sigma);
     }
     delete ga;
     return SGMM_OK;
@@ -287,20 +286,9 @@ int sgmm_ga_select(sgmm_ga* ga, const sgmm_bundle* val, void* stream)
     one.genomes = ga->mm_master; one.master = nullptr; one.count = 1;          // the new master IS the best child
     if (c.hidden == 256) {                                                     // no exact kernel at this width: same tensor-core path
         if (int rc = launch_spec256(val, one, c.phi, c.fee_rate, ga->val_fit, ga->val_trd, nullptr, nullptr, st)) return rc;
-    } else {
-        // the new master on the validation bundle, adversary off (drl_engine.py:129-140): policy for every (bar, inventory)
-        // in parallel + automaton scan + reference-order sum (sgmm_one.cu), bit-identical to the sequential kernel
-        const size_t need = rollout_one_scratch_bytes(val->T);
-        if (ga->val_scratch_bytes < need) {
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            if (st) cudaStreamIsCapturing(st, &cap);
-            if (cap != cudaStreamCaptureStatusNone) { set_error("run one generation on this validation bundle outside the stream capture first (its policy table is allocated on first use)"); return SGMM_ERR_INVALID; }
-            cudaFree(ga->val_scratch); ga->val_scratch = nullptr; ga->val_scratch_bytes = 0;      // cudaFree synchronises: no user left
-            if (int rc = check_cuda(cudaMalloc(&ga->val_scratch, need), "cudaMalloc(validation policy table)")) return rc;
-            ga->val_scratch_bytes = need;
-        }
-        if (int rc = launch_rollout_one(val, ga->mm_master, c.phi, c.fee_rate, ga->val_scratch, ga->val_fit, ga->val_trd, st)) return rc;
-    }
+    } else if (int rc = launch_rollout(val, one, nullptr, c.hidden, c.phi, c.fee_rate, 0, 0, ga->val_fit, ga->val_trd, st)) return rc;
+    // (one individual, adversary off: launch_rollout takes the small-population path of sgmm_one.cu -- policy for every
+    //  (bar, inventory) in parallel, automaton scan, reference-order sum; bit-identical to the sequential kernel)
     ga_update_kernel<<<1, 256, 0, st>>>(ga->st, ga->val_fit, ga->val_trd, ga->mm_master, ga->best_master, ga->G,
                                         c.patience, c.use_arl, c.max_generations, ga->h_train_f, ga->h_val_f,
                                         ga->h_train_t, ga->h_val_t, ga->h_sigma);

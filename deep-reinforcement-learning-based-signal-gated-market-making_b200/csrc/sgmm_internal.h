@@ -118,10 +118,9 @@ inline int opt_in_smem(Kernel kern, size_t bytes, std::atomic<uint64_t>& mask, c
 int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, int hidden,
                    double phi, double fee, int units_per_lane, int warps_per_cta,
                    double* fitness, int32_t* trades, cudaStream_t st);
-// one individual's episode, fast (sgmm_one.cu): the GA's validation rollout
-size_t rollout_one_scratch_bytes(int64_t T);
-int launch_rollout_one(const sgmm_bundle* b, const float* genome, double phi, double fee, void* scratch, double* fitness,
-                       int32_t* trades, cudaStream_t st);
+// small populations, fast (sgmm_one.cu): policy table for every (bar, inventory) + automaton scan + reference-order sum
+constexpr int64_t SMALL_POP_MAX = 100;      // measured break-even against the sequential kernel: ~115 individuals (profiles/r2_small_population_path.log)
+int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades, cudaStream_t st);
 int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const float* adv_genome,
                  const int32_t* forced, const int32_t* table, double phi, double fee, const sgmm_trace* tr,
                  double* fitness, int32_t* trades, cudaStream_t st);

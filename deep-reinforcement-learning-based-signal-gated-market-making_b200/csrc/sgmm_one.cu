@@ -1,9 +1,10 @@
-// sgmm_one.cu -- ONE individual's episode, fast: the validation rollout of a GA generation (Env/drl_engine.py:129-140:
-// the generation's best child on the validation bundle, adversary off) and any other single-policy episode.
+// sgmm_one.cu -- SMALL populations, fast: the validation rollout of a GA generation (Env/drl_engine.py:129-140: the
+// generation's best child on the validation bundle, adversary off), a single evaluate_individual call, and populations
+// of the reference's own size (pop_size = 50, Env/drl_engine.py:70).
 //
-// The population kernel gives an individual one warp (or eight lanes) and walks the bars one after the other: for a
-// single individual that is one latency-bound warp on one SM (2 880 bars = 0.64 ms, 13 % of a 4096-individual
-// generation; at the reference's own scale -- population 50, one day -- as long as the population rollout itself).
+// The population kernel gives an individual one warp (or eight lanes) and walks the bars one after the other: below a
+// few hundred individuals that is a handful of latency-bound warps on an otherwise idle GPU (one individual x 2 880
+// bars = 0.64 ms, 13 % of a 4096-individual generation; 50 individuals x 14 400 bars = 2.5 ms = 0.29 G env-steps/s).
 // With no adversary the action at bar t depends on (t, inventory) only and the inventory has five values
 // (SURVEY.md 7.3), so the episode splits into
 //   1. policy_table_kernel  the exact policy (SGMM-F32 order, identical instruction sequence to trace_kernel_h32) for
@@ -13,8 +14,10 @@
 //                           composition (every bar is a map {0..4} -> {0..4}; composition is associative), then the fp64
 //                           half for the visited pairs in parallel, and the one thing that is inherently serial -- the
 //                           reference-order fp64 reward sum (drl_engine.py:54) -- by one thread, chunk by chunk.
-// 5x the policy FLOPs of the sequential walk, ~10x less time; results bit-identical to rollout_kernel_h32 (the GA
-// parity tests compare the whole history with the oracle's).
+// 5x the policy FLOPs of the sequential walk, ~10x less time; results bit-identical to rollout_kernel_h32
+// (tests/test_gpu_configs.py compares both with the oracle; the GA parity tests compare whole histories).  One CTA of
+// walk_account_kernel per individual; the launcher takes this path below SMALL_POP_MAX individuals (measured break-even
+// against the sequential kernel: profiles/r2_small_population_path.log).
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
 #include "sgmm_step_core.h"
@@ -32,53 +35,76 @@ struct Scratch {                           // per (bar, inventory index) pair, w
     uint8_t* next;                         // [T][8]  next inventory index (bytes 0..4)
 };
 
-__global__ void __launch_bounds__(128) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const float* __restrict__ genome,
+constexpr int PAIRS_PER_TASK_MAX = 160;   // (bar, inventory) pairs a warp evaluates per task: the launcher shrinks tasks of small problems
+                                          // until the whole GPU has work (a lone warp needs ~330 cycles per pair: shuffle latency)
+
+__global__ void __launch_bounds__(128) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const PopArgs mm_in, int PAIRS_PER_TASK,
                                                             float2* __restrict__ code, uint8_t* __restrict__ next)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    // weights of hidden unit `lane` (models/model.py:31-36 layout), exactly as trace_kernel_h32 holds them
-    const int j = lane;
-    const float w1x = __ldg(genome + 3 * j), w1y = __ldg(genome + 3 * j + 1), w1i = __ldg(genome + 3 * j + 2);
-    const float b1 = __ldg(genome + 3 * H + j), b2 = __ldg(genome + 4 * H + H * H + j);
-    const float w3a = __ldg(genome + 5 * H + H * H + j), w3b = __ldg(genome + 6 * H + H * H + j);
-    const float b3a = __ldg(genome + 7 * H + H * H), b3b = __ldg(genome + 7 * H + H * H + 1);
+    const PopArgs mm = resolve(mm_in);
+    constexpr int64_t G = (int64_t)H * H + 7 * H + 2;
+    const int64_t pairs = T * 5, tasks_per_ind = (pairs + PAIRS_PER_TASK - 1) / PAIRS_PER_TASK, ntasks = mm.count * tasks_per_ind;
+    const int j = lane;                        // hidden unit of this lane (models/model.py:31-36 layout), as in trace_kernel_h32
+    float w1x = 0, w1y = 0, w1i = 0, b1 = 0, b2 = 0, w3a = 0, w3b = 0, b3a = 0, b3b = 0;
     float w2[32];
+    int64_t loaded = -1;
+    // contiguous blocks of tasks per warp: consecutive tasks belong to the same individual, whose weights stay in registers
+    const int64_t per_warp = (ntasks + nwarps - 1) / nwarps;
+    const int64_t task_lo = warp * per_warp, task_hi = task_lo + per_warp < ntasks ? task_lo + per_warp : ntasks;
+    for (int64_t task = task_lo; task < task_hi; ++task) {
+        const int64_t ind = task / tasks_per_ind;
+        if (ind != loaded) {
+            const GenomeSource src = make_source(mm, ind, G);
+            w1x = src.at(3 * j); w1y = src.at(3 * j + 1); w1i = src.at(3 * j + 2);
+            b1 = src.at(3 * H + j); b2 = src.at(4 * H + H * H + j);
+            w3a = src.at(5 * H + H * H + j); w3b = src.at(6 * H + H * H + j);
+            b3a = src.at(7 * H + H * H); b3b = src.at(7 * H + H * H + 1);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) w2[k] = __ldg(genome + 4 * H + j * H + k);
-    for (int64_t p = warp; p < T * 5; p += nwarps) {
-        const int64_t t = p / 5;
-        const int iv = (int)(p - t * 5);
-        const float4 sg = *reinterpret_cast<const float4*>(&sig[t]);              // z1, z2, tha, thb
-        const float inv2 = (float)(iv - 2) * 0.5f;                                 // drl_engine.py:35
-        // ---- TradingPolicy.forward in SGMM-F32 order (models/model.py:9-15) ----
-        float v = __fmaf_rn(w1x, sg.x, b1);
-        v = __fmaf_rn(w1y, sg.y, v);
-        v = __fmaf_rn(w1i, inv2, v);
-        const float h1 = fmaxf(v, 0.0f);
-        float c0 = b2, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-            c0 = __fmaf_rn(w2[k + 0], __shfl_sync(0xffffffffu, h1, k + 0), c0);
-            c1 = __fmaf_rn(w2[k + 1], __shfl_sync(0xffffffffu, h1, k + 1), c1);
-            c2 = __fmaf_rn(w2[k + 2], __shfl_sync(0xffffffffu, h1, k + 2), c2);
-            c3 = __fmaf_rn(w2[k + 3], __shfl_sync(0xffffffffu, h1, k + 3), c3);
+            for (int c = 0; c < 8; ++c) {
+                float v4[4]; src.at4(4 * H + (int64_t)j * H + 4 * c, v4);
+                w2[4 * c] = v4[0]; w2[4 * c + 1] = v4[1]; w2[4 * c + 2] = v4[2]; w2[4 * c + 3] = v4[3];
+            }
+            loaded = ind;
         }
-        const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)), 0.0f);
-        float ra = __fmul_rn(w3a, h2), rb = __fmul_rn(w3b, h2);
+        const int64_t p_lo = (task - ind * tasks_per_ind) * PAIRS_PER_TASK, p_hi = p_lo + PAIRS_PER_TASK < pairs ? p_lo + PAIRS_PER_TASK : pairs;
+        float2* codei = code + ind * pairs;
+        uint8_t* nexti = next + ind * T * 8;
+        for (int64_t p = p_lo; p < p_hi; ++p) {
+            const int64_t t = p / 5;
+            const int iv = (int)(p - t * 5);
+            const float4 sg = *reinterpret_cast<const float4*>(&sig[t]);              // z1, z2, tha, thb
+            const float inv2 = (float)(iv - 2) * 0.5f;                                 // drl_engine.py:35
+            // ---- TradingPolicy.forward in SGMM-F32 order (models/model.py:9-15) ----
+            float v = __fmaf_rn(w1x, sg.x, b1);
+            v = __fmaf_rn(w1y, sg.y, v);
+            v = __fmaf_rn(w1i, inv2, v);
+            const float h1 = fmaxf(v, 0.0f);
+            float c0 = b2, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            ra = __fadd_rn(ra, __shfl_xor_sync(0xffffffffu, ra, m));
-            rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
-        }
-        const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);                      // raw*5.0 (drl_engine.py:39)
-        const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
-        // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
-        const bool fb = (inv2 < 1.0f) && (qb < sg.w);                              // market_env.py:34,37
-        const bool fs = (inv2 > -1.0f) && (qa < sg.z);                             // :35,:38
-        if (lane == 0) {
-            code[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
-            next[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));        // :45,:51
+            for (int k = 0; k < 32; k += 4) {
+                c0 = __fmaf_rn(w2[k + 0], __shfl_sync(0xffffffffu, h1, k + 0), c0);
+                c1 = __fmaf_rn(w2[k + 1], __shfl_sync(0xffffffffu, h1, k + 1), c1);
+                c2 = __fmaf_rn(w2[k + 2], __shfl_sync(0xffffffffu, h1, k + 2), c2);
+                c3 = __fmaf_rn(w2[k + 3], __shfl_sync(0xffffffffu, h1, k + 3), c3);
+            }
+            const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)), 0.0f);
+            float ra = __fmul_rn(w3a, h2), rb = __fmul_rn(w3b, h2);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                ra = __fadd_rn(ra, __shfl_xor_sync(0xffffffffu, ra, m));
+                rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
+            }
+            const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);                      // raw*5.0 (drl_engine.py:39)
+            const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
+            // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
+            const bool fb = (inv2 < 1.0f) && (qb < sg.w);                              // market_env.py:34,37
+            const bool fs = (inv2 > -1.0f) && (qa < sg.z);                             // :35,:38
+            if (lane == 0) {
+                codei[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
+                nexti[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));       // :45,:51
+            }
         }
     }
 }
@@ -94,10 +120,12 @@ __device__ __forceinline__ uint32_t map_then(uint32_t f, uint32_t g)
 }
 constexpr uint32_t MAP_ID = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
 
-__global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_kernel(const BarPx* __restrict__ px, int64_t T, const float2* __restrict__ code,
-                                                                         const uint8_t* __restrict__ next, double tick, double phi, double fee,
+__global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_kernel(const BarPx* __restrict__ px, int64_t T, const float2* __restrict__ code_all,
+                                                                         const uint8_t* __restrict__ next_all, double tick, double phi, double fee,
                                                                          double* __restrict__ fitness, int32_t* __restrict__ trades)
 {
+    const float2* code = code_all + (int64_t)blockIdx.x * T * 5;          // one CTA per individual
+    const uint8_t* next = next_all + (int64_t)blockIdx.x * T * 8;
     __shared__ uint32_t s_warp[32];
     __shared__ int s_trades;
     __shared__ double s_rew[SUM_CHUNK];
@@ -172,33 +200,43 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_kernel(const Bar
     if (tid == 0) {
         const int n = s_trades;
         if (n == 0) total = sub_rn(total, 50.0);                                   // drl_engine.py:64-65
-        *fitness = total; *trades = n;
+        fitness[blockIdx.x] = total; trades[blockIdx.x] = n;
     }
 }
 
 }  // namespace one
 
-size_t rollout_one_scratch_bytes(int64_t T) { return (size_t)T * (5 * sizeof(float2) + 8) + 256; }
-
-// One individual's episode on `b` (explicit genome, H = 32, no adversary) through the two kernels above.  `scratch`:
-// rollout_one_scratch_bytes(b->T) bytes of device memory owned by the caller.
-int launch_rollout_one(const sgmm_bundle* b, const float* genome, double phi, double fee, void* scratch, double* fitness,
-                       int32_t* trades, cudaStream_t st)
+// Episodes of a small population on `b` (H = 32, exact SGMM-F32 order, no adversary) through the two kernels above.  The
+// policy table ([count][T] x 48 B) lives in the bundle's grow-only code buffer (sgmm_account.cu: rollouts sharing it are
+// ordered across streams; the first rollout of a size allocates and must not run under a stream capture).
+int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades, cudaStream_t st)
 {
     using namespace one;
-    const int64_t T = b->T;
-    float2* code = reinterpret_cast<float2*>(scratch);
-    uint8_t* next = reinterpret_cast<uint8_t*>(code + (T * 5 + 15) / 16 * 16);
+    const int64_t T = b->T, P = mm.count;
+    if (P == 0) return SGMM_OK;
+    uint64_t* buf = nullptr;
+    if (int rc = reserve_codes(b, P * 6 + 1, st, &buf)) return rc;               // 48 B per (individual, bar) + slack for T == 0
+    float2* code = reinterpret_cast<float2*>(buf);
+    uint8_t* next = reinterpret_cast<uint8_t*>(code + P * T * 5);
     if (T > 0) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
-        const int64_t pairs = T * 5, warps_wanted = (pairs + 3) / 4;               // ~4 pairs per warp: latency, not throughput
-        const int64_t blocks = (warps_wanted + 3) / 4 < (int64_t)sms * 8 ? (warps_wanted + 3) / 4 : (int64_t)sms * 8;
-        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 128, 0, st>>>(b->sig, T, genome, code, next);
+        // task size: enough tasks for ~16 warps per SM, but not so small that reloading an individual's weights (seeded
+        // children: ~45 Philox calls per lane) outweighs the evaluations
+        const int64_t want_tasks = (int64_t)sms * 64;
+        int64_t ppt = (P * T * 5 + want_tasks - 1) / want_tasks;
+        const int64_t ppt_min = mm.genomes ? 8 : 40;
+        if (ppt < ppt_min) ppt = ppt_min;
+        if (ppt > PAIRS_PER_TASK_MAX) ppt = PAIRS_PER_TASK_MAX;
+        const int64_t ntasks = P * ((T * 5 + ppt - 1) / ppt);
+        int64_t blocks = (ntasks + 3) / 4;                                         // 4 warps per block, one task per warp at least
+        if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 128, 0, st>>>(b->sig, T, mm, (int)ppt, code, next);
         if (int rc = check_cuda(cudaGetLastError(), "policy_table_kernel launch")) return rc;
     }
-    walk_account_kernel<<<1, WALK_THREADS, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
-    return check_cuda(cudaGetLastError(), "walk_account_kernel launch");
+    walk_account_kernel<<<(unsigned)P, WALK_THREADS, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
+    if (int rc = check_cuda(cudaGetLastError(), "walk_account_kernel launch")) return rc;
+    return release_codes(b, st);
 }
 
 }  // namespace sgmm
