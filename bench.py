@@ -551,6 +551,30 @@ def run_ours(args):
         sh.ga.close(); ref.close()
         return bool(flag.item())
 
+    def config0():
+        """The reference's own scale (configs[0]): population 50 (Env/drl_engine.py:70), no fee, phi 1e-4 -- one day and the
+        15-day training set of the replication report; seeded children, CUDA-graph replay (device time, rank 0's GPU)."""
+        out = {"workload": "configs[0]: population 50, H=32, no fee, phi=1e-4; one synthetic day (240 bars) and 15 days (3600 bars)"}
+        md = torch.from_numpy(master).to(dev)
+        for days in (1, 15):
+            b0 = synthetic.synthetic_bundle(days, first_day=200)
+            bun0 = sgmm_b200.Bundle.from_arrays(b0, synthetic.train_stats_of(b0), TICK, device=local)
+            run = lambda: sgmm_b200.rollout_seeded(bun0, md, count=50, sigma=0.05, seed=1, generation=0, phi=PHI)      # noqa: E731
+            run(); run(); torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(10):
+                    run()
+            gr.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            out[f"{days}_day"] = {"bars": bun0.T, "ms_per_rollout": ms, "value": 50 * bun0.T / ms * 1e3, "unit": UNIT}
+            bun0.close()
+        return out
+
+    if world == 1:
+        guarded("config0_reference_scale", config0)
     guarded("config3_adversarial", config3)
     if world == 1:
         guarded("config4_h256_fee", config4)
