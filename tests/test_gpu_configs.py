@@ -417,3 +417,18 @@ def test_validation_fast_path_is_bit_identical_to_the_sequential_kernel_and_the_
     assert h["val_trades"][1] == t.item() == to
     if T >= 240:
         assert to > 0
+
+
+@pytest.mark.parametrize("name", ["plain", "arl", "fee", "arl_fee"])
+def test_cuda_matches_the_committed_long_reference_vectors(sg, orc, name):
+    """tests/golden/ref_long.npz: the unmodified reference on 8 individuals x 14 400 bars (oracle/make_golden_long.py) --
+    the config-2 length pinned by committed vectors, with every trajectory's minimum rounding margin logged."""
+    from test_oracle_golden import _long_case, check_against_long_reference
+    bundle, stats, genomes, adv, fee, f_ref, t_ref = _long_case(name)
+    bun = sg.Bundle.from_arrays(bundle, stats, 0.001)
+    fit, trd = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), None if adv is None else torch.from_numpy(adv).cuda(),
+                                     phi=1e-4, fee_rate=fee, units_per_lane=4)                       # the population kernel
+    check_against_long_reference(name, fit.cpu().numpy(), trd.cpu().numpy(), orc)
+    if adv is None:                                                                                  # and the small-population path
+        f2, t2 = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, fee_rate=fee)
+        assert torch.equal(f2, fit) and torch.equal(t2, trd)
