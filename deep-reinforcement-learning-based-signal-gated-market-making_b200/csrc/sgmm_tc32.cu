@@ -26,7 +26,13 @@
 // Measured (profiles/r2_tc32_v*_bench.log, 4096 x 14 400): the walker must stay tiny -- it is ONE warp on a scheduler it
 // shares with six busy conversion warps: doing the fp64 half of the visited rows in the walker (40 instructions per bar)
 // ran at 19 ms, the marks scheme at 4.9 ms without / 6.3 ms with the adversary, leg-table rewards for every row in E3
-// at 3.8 / 16.5 ms, against 2.4 ms for the plain path below -- which therefore stays as it was in round 1.  The
+// at 3.8 / 16.5 ms, leg records staged per chunk into a shared-memory ring by TMA (two shared loads + two fp64 adds per
+// row, literal expression under a warp vote outside the record) at 3.6 ms, against 2.4 ms for the plain path below -- which
+// therefore stays as it was in round 1.  The common cause: with less fp64 in E3 the MMA stream gets denser and the
+// walker's 25 dependent fp64 adds per chunk -- the one piece of fp64 that cannot leave the kernel without 8 B of HBM traffic
+// per env-step -- starve behind it (an fp64 instruction waits for a gap in tcgen05.mma activity, profiles/r1_fp64_under_mma.txt);
+// with NO fp64 at all the kernel runs at 2.30 ms (profiles/r2_tc32_dbg1.log, dbg=1), i.e. fp64 costs 5 %, not the factor
+// the shared-pipe counter suggests.  The
 // adversary path is correct (tests/test_gpu_tc32.py) but not faster than the exact kernel (6.3 vs 5.3 ms): without its
 // accounting it still takes 4.9 ms, with one combination instead of four 4.3 ms (profiles/r2_tc32_dbg2.log) -- the extra
 // walker -> E3 -> walker round trip per chunk stalls the D3 drain, i.e. the MMA pipeline.
