@@ -7,9 +7,10 @@
 // bars = 0.64 ms, 13 % of a 4096-individual generation; 50 individuals x 14 400 bars = 2.5 ms = 0.29 G env-steps/s).
 // With no adversary the action at bar t depends on (t, inventory) only and the inventory has five values
 // (SURVEY.md 7.3), so the episode splits into
-//   1. policy_table_kernel  the exact policy (SGMM-F32 order, identical instruction sequence to trace_kernel_h32) for
-//                           EVERY (bar, inventory) pair -- 5 T independent evaluations spread over the whole GPU -- and
-//                           the integer half of the env step of the pair: fills, next inventory, 8-byte step code;
+//   1. policy_table_kernel  the exact policy (SGMM-F32 order: the operations of trace_kernel_h32 in the same order) for
+//                           EVERY (bar, inventory) pair -- 5 T independent evaluations spread over the whole GPU, one pair
+//                           per thread with the weights broadcast from shared memory -- and the integer half of the env
+//                           step of the pair: fills, next inventory, 8-byte step code;
 //   2. walk_account_kernel  one CTA: the walk through the 5-state automaton as a parallel prefix scan over function
 //                           composition (every bar is a map {0..4} -> {0..4}; composition is associative), then the fp64
 //                           half for the visited pairs in parallel, and the one thing that is inherently serial -- the
@@ -27,7 +28,6 @@ namespace sgmm {
 namespace one {
 
 constexpr int H = 32;
-constexpr int WALK_THREADS = 1024;
 constexpr int SUM_CHUNK = 2048;            // bars whose rewards sit in shared memory while one thread sums them
 
 struct Scratch {                           // per (bar, inventory index) pair, written by policy_table_kernel
@@ -35,76 +35,101 @@ struct Scratch {                           // per (bar, inventory index) pair, w
     uint8_t* next;                         // [T][8]  next inventory index (bytes 0..4)
 };
 
-constexpr int PAIRS_PER_TASK_MAX = 160;   // (bar, inventory) pairs a warp evaluates per task: the launcher shrinks tasks of small problems
-                                          // until the whole GPU has work (a lone warp needs ~330 cycles per pair: shuffle latency)
+constexpr int PT_THREADS = 128;           // policy_table_kernel: one (bar, inventory) pair per thread, one individual per block task
 
-__global__ void __launch_bounds__(128) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const PopArgs mm_in, int PAIRS_PER_TASK,
-                                                            float2* __restrict__ code, uint8_t* __restrict__ next)
+// The individual's weights as the block stages them in shared memory: per hidden unit j one float4 {W1[j,0], W1[j,1], W1[j,2],
+// b1[j]}, W2 row-major, b2, W3 as float2 {W3[0,j], W3[1,j]}, b3.  Every lane reads the SAME address at a time (a broadcast:
+// one wavefront per load), so the policy of 32 different pairs costs the shared-memory traffic of one.
+struct PtSmem {
+    float4 l1[H];
+    float w2[H][H];
+    float b2[H];
+    float2 w3[H];
+    float b3[2];
+};
+
+// One (bar, inventory) pair per THREAD, the individual's weights broadcast from shared memory: ~1 700 instructions per pair
+// and thread, i.e. ~53 warp instructions per pair instead of the ~110 (42 of them shuffles) of the lane-per-hidden-unit
+// mapping, FMA-pipe bound instead of shuffle bound.  Same operations in the same order as trace_kernel_h32 (SGMM-F32
+// order): layer 1 fma chain from b1; layer 2 four chains over k mod 4 from (b2, 0, 0, 0), combined (c0+c2)+(c1+c3); layer 3
+// products summed by the xor-butterfly tree 16, 8, 4, 2, 1 (written out serially: s[l] = s[l] + s[l + m]) plus b3.
+__global__ void __launch_bounds__(PT_THREADS) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const PopArgs mm_in, int64_t pairs_per_task,
+                                                                   float2* __restrict__ code, uint8_t* __restrict__ next)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ PtSmem sm;
     const PopArgs mm = resolve(mm_in);
     constexpr int64_t G = (int64_t)H * H + 7 * H + 2;
-    const int64_t pairs = T * 5, tasks_per_ind = (pairs + PAIRS_PER_TASK - 1) / PAIRS_PER_TASK, ntasks = mm.count * tasks_per_ind;
-    const int j = lane;                        // hidden unit of this lane (models/model.py:31-36 layout), as in trace_kernel_h32
-    float w1x = 0, w1y = 0, w1i = 0, b1 = 0, b2 = 0, w3a = 0, w3b = 0, b3a = 0, b3b = 0;
-    float w2[32];
+    const int64_t pairs = T * 5, tasks_per_ind = (pairs + pairs_per_task - 1) / pairs_per_task, ntasks = mm.count * tasks_per_ind;
     int64_t loaded = -1;
-    // contiguous blocks of tasks per warp: consecutive tasks belong to the same individual, whose weights stay in registers
-    const int64_t per_warp = (ntasks + nwarps - 1) / nwarps;
-    const int64_t task_lo = warp * per_warp, task_hi = task_lo + per_warp < ntasks ? task_lo + per_warp : ntasks;
-    for (int64_t task = task_lo; task < task_hi; ++task) {
+    for (int64_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
         const int64_t ind = task / tasks_per_ind;
-        if (ind != loaded) {
+        if (ind != loaded) {                                   // (consecutive tasks of a block usually belong to different individuals)
+            __syncthreads();
             const GenomeSource src = make_source(mm, ind, G);
-            w1x = src.at(3 * j); w1y = src.at(3 * j + 1); w1i = src.at(3 * j + 2);
-            b1 = src.at(3 * H + j); b2 = src.at(4 * H + H * H + j);
-            w3a = src.at(5 * H + H * H + j); w3b = src.at(6 * H + H * H + j);
-            b3a = src.at(7 * H + H * H); b3b = src.at(7 * H + H * H + 1);
+            for (int q = threadIdx.x; q < 313; q += PT_THREADS) {                 // genome in groups of four elements (models/model.py:31-36 layout)
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (q < 312) src.at4(4 * q, v); else { v[0] = src.at(1248); v[1] = src.at(1249); }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float v4[4]; src.at4(4 * H + (int64_t)j * H + 4 * c, v4);
-                w2[4 * c] = v4[0]; w2[4 * c + 1] = v4[1]; w2[4 * c + 2] = v4[2]; w2[4 * c + 3] = v4[3];
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * q + i;
+                    if (e < 96) reinterpret_cast<float*>(&sm.l1[e / 3])[e % 3] = v[i];                   // W1[j, i]
+                    else if (e < 128) sm.l1[e - 96].w = v[i];                                              // b1[j]
+                    else if (e < 1152) sm.w2[(e - 128) >> 5][(e - 128) & 31] = v[i];                       // W2[j, k]
+                    else if (e < 1184) sm.b2[e - 1152] = v[i];
+                    else if (e < 1248) reinterpret_cast<float*>(&sm.w3[(e - 1184) & 31])[(e - 1184) >> 5] = v[i];   // W3[o, j]
+                    else if (e < 1250) sm.b3[e - 1248] = v[i];
+                }
             }
+            __syncthreads();
             loaded = ind;
         }
-        const int64_t p_lo = (task - ind * tasks_per_ind) * PAIRS_PER_TASK, p_hi = p_lo + PAIRS_PER_TASK < pairs ? p_lo + PAIRS_PER_TASK : pairs;
+        const int64_t p_lo = (task - ind * tasks_per_ind) * pairs_per_task, p_hi = p_lo + pairs_per_task < pairs ? p_lo + pairs_per_task : pairs;
         float2* codei = code + ind * pairs;
         uint8_t* nexti = next + ind * T * 8;
-        for (int64_t p = p_lo; p < p_hi; ++p) {
+        for (int64_t p = p_lo + threadIdx.x; p < p_hi; p += PT_THREADS) {
             const int64_t t = p / 5;
             const int iv = (int)(p - t * 5);
-            const float4 sg = *reinterpret_cast<const float4*>(&sig[t]);              // z1, z2, tha, thb
-            const float inv2 = (float)(iv - 2) * 0.5f;                                 // drl_engine.py:35
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(&sig[t]));          // z1, z2, tha, thb
+            const float inv2 = (float)(iv - 2) * 0.5f;                                     // drl_engine.py:35
             // ---- TradingPolicy.forward in SGMM-F32 order (models/model.py:9-15) ----
-            float v = __fmaf_rn(w1x, sg.x, b1);
-            v = __fmaf_rn(w1y, sg.y, v);
-            v = __fmaf_rn(w1i, inv2, v);
-            const float h1 = fmaxf(v, 0.0f);
-            float c0 = b2, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+            float h1[H];
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                c0 = __fmaf_rn(w2[k + 0], __shfl_sync(0xffffffffu, h1, k + 0), c0);
-                c1 = __fmaf_rn(w2[k + 1], __shfl_sync(0xffffffffu, h1, k + 1), c1);
-                c2 = __fmaf_rn(w2[k + 2], __shfl_sync(0xffffffffu, h1, k + 2), c2);
-                c3 = __fmaf_rn(w2[k + 3], __shfl_sync(0xffffffffu, h1, k + 3), c3);
+            for (int j = 0; j < H; ++j) {
+                const float4 w = sm.l1[j];
+                float v = __fmaf_rn(w.x, sg.x, w.w);
+                v = __fmaf_rn(w.y, sg.y, v);
+                v = __fmaf_rn(w.z, inv2, v);
+                h1[j] = fmaxf(v, 0.0f);
             }
-            const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)), 0.0f);
-            float ra = __fmul_rn(w3a, h2), rb = __fmul_rn(w3b, h2);
+            float pa[H], pb[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float c0 = sm.b2[j], c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < H; k += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(&sm.w2[j][k]);
+                    c0 = __fmaf_rn(w.x, h1[k + 0], c0);
+                    c1 = __fmaf_rn(w.y, h1[k + 1], c1);
+                    c2 = __fmaf_rn(w.z, h1[k + 2], c2);
+                    c3 = __fmaf_rn(w.w, h1[k + 3], c3);
+                }
+                const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)), 0.0f);
+                const float2 w3 = sm.w3[j];
+                pa[j] = __fmul_rn(w3.x, h2);
+                pb[j] = __fmul_rn(w3.y, h2);
+            }
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
-                ra = __fadd_rn(ra, __shfl_xor_sync(0xffffffffu, ra, m));
-                rb = __fadd_rn(rb, __shfl_xor_sync(0xffffffffu, rb, m));
+#pragma unroll
+                for (int l = 0; l < m; ++l) { pa[l] = __fadd_rn(pa[l], pa[l + m]); pb[l] = __fadd_rn(pb[l], pb[l + m]); }
             }
-            const float qa = __fmul_rn(__fadd_rn(ra, b3a), 5.0f);                      // raw*5.0 (drl_engine.py:39)
-            const float qb = __fmul_rn(__fadd_rn(rb, b3b), 5.0f);
+            const float qa = __fmul_rn(__fadd_rn(pa[0], sm.b3[0]), 5.0f);                  // raw*5.0 (drl_engine.py:39)
+            const float qb = __fmul_rn(__fadd_rn(pb[0], sm.b3[1]), 5.0f);
             // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
-            const bool fb = (inv2 < 1.0f) && (qb < sg.w);                              // market_env.py:34,37
-            const bool fs = (inv2 > -1.0f) && (qa < sg.z);                             // :35,:38
-            if (lane == 0) {
-                codei[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
-                nexti[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));       // :45,:51
-            }
+            const bool fb = (inv2 < 1.0f) && (qb < sg.w);                                  // market_env.py:34,37
+            const bool fs = (inv2 > -1.0f) && (qa < sg.z);                                 // :35,:38
+            codei[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
+            nexti[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));               // :45,:51
         }
     }
 }
@@ -120,13 +145,16 @@ __device__ __forceinline__ uint32_t map_then(uint32_t f, uint32_t g)
 }
 constexpr uint32_t MAP_ID = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
 
-__global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_kernel(const BarPx* __restrict__ px, int64_t T, const float2* __restrict__ code_all,
+// WALK_THREADS = 1024 (one individual per SM: shortest latency, populations up to the SM count) or 512 (three per SM: the
+// serial reward sum of one individual hides behind the others)
+template <int WALK_THREADS>
+__global__ void __launch_bounds__(WALK_THREADS, WALK_THREADS == 1024 ? 1 : 3) walk_account_kernel(const BarPx* __restrict__ px, int64_t T, const float2* __restrict__ code_all,
                                                                          const uint8_t* __restrict__ next_all, double tick, double phi, double fee,
                                                                          double* __restrict__ fitness, int32_t* __restrict__ trades)
 {
     const float2* code = code_all + (int64_t)blockIdx.x * T * 5;          // one CTA per individual
     const uint8_t* next = next_all + (int64_t)blockIdx.x * T * 8;
-    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_warp[32];                         // (WALK_THREADS / 32 entries used)
     __shared__ int s_trades;
     __shared__ double s_rew[SUM_CHUNK];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -146,7 +174,7 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_kernel(const Bar
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = s_warp[lane];
+        uint32_t w = lane < WALK_THREADS / 32 ? s_warp[lane] : MAP_ID;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
@@ -221,20 +249,21 @@ int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, double phi, do
     if (T > 0) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
-        // task size: enough tasks for ~16 warps per SM, but not so small that reloading an individual's weights (seeded
-        // children: ~45 Philox calls per lane) outweighs the evaluations
-        const int64_t want_tasks = (int64_t)sms * 64;
-        int64_t ppt = (P * T * 5 + want_tasks - 1) / want_tasks;
-        const int64_t ppt_min = mm.genomes ? 8 : 40;
+        // task = (individual, range of pairs): ranges of whole 128-pair rounds, sized so that the GPU gets ~8 blocks per SM
+        const int64_t want_blocks = (int64_t)sms * 8;
+        int64_t ppt = (P * T * 5 + want_blocks - 1) / want_blocks;
+        ppt = (ppt + PT_THREADS - 1) / PT_THREADS * PT_THREADS;
+        const int64_t ppt_min = mm.genomes ? PT_THREADS : 4 * PT_THREADS;      // seeded children: staging costs ~10 Philox calls per thread
         if (ppt < ppt_min) ppt = ppt_min;
-        if (ppt > PAIRS_PER_TASK_MAX) ppt = PAIRS_PER_TASK_MAX;
         const int64_t ntasks = P * ((T * 5 + ppt - 1) / ppt);
-        int64_t blocks = (ntasks + 3) / 4;                                         // 4 warps per block, one task per warp at least
-        if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 128, 0, st>>>(b->sig, T, mm, (int)ppt, code, next);
+        const int64_t blocks = ntasks < want_blocks * 2 ? ntasks : want_blocks * 2;
+        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), PT_THREADS, 0, st>>>(b->sig, T, mm, ppt, code, next);
         if (int rc = check_cuda(cudaGetLastError(), "policy_table_kernel launch")) return rc;
     }
-    walk_account_kernel<<<(unsigned)P, WALK_THREADS, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
+    int sms2 = 148;
+    cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, b->device);
+    if (P <= sms2) walk_account_kernel<1024><<<(unsigned)P, 1024, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
+    else walk_account_kernel<512><<<(unsigned)P, 512, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
     if (int rc = check_cuda(cudaGetLastError(), "walk_account_kernel launch")) return rc;
     return release_codes(b, st);
 }

@@ -507,10 +507,7 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
     // small populations without an adversary: the policy-table path (sgmm_one.cu) unless the caller pinned a geometry
     {
         static const int64_t small_max = [] { const char* e = getenv("SGMM_SMALL_POP_MAX"); return e ? (int64_t)atoll(e) : SMALL_POP_MAX; }();
-        // measured break-even (profiles/r2_small_population_path.log, graph replay): ~115 individuals for episodes of 1000+ bars,
-        // ~50 for one day of 240 bars (there the walk kernel's fixed cost weighs more)
-        const int64_t by_length = 32 + b->T / 12;
-        if (!adv && units_per_lane == 0 && warps_per_cta == 0 && mm.count <= (by_length < small_max ? by_length : small_max))
+        if (!adv && units_per_lane == 0 && warps_per_cta == 0 && mm.count <= small_max)
             return launch_rollout_small(b, mm, phi, fee, fitness, trades, st);
     }
     int dev = b->device;

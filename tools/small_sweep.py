@@ -6,10 +6,10 @@ import numpy as np, torch, sgmm_b200
 from sgmm_b200 import synthetic
 tag = sys.argv[1]
 out = {}
-for days in (1, 2, 4, 12, 60):
+for days in (1, 4, 12, 60):
     bundle = synthetic.synthetic_bundle(days)
     bun = sgmm_b200.Bundle.from_arrays(bundle, synthetic.train_stats_of(bundle), 0.001)
-    for P in (1, 8, 25, 50, 75, 100, 148, 192, 256):
+    for P in (1, 8, 25, 50, 100, 148, 200, 256, 288, 320, 400, 500):
         m, genomes = synthetic.policy_like_genomes(P, seed=0)
         g = torch.from_numpy(genomes).cuda(); md = torch.from_numpy(m).cuda()
         for kind, run in (("explicit", lambda: sgmm_b200.rollout_population(bun, g, phi=1e-4)),
