@@ -433,7 +433,7 @@ def run_ours(args):
     val = sgmm_b200.Bundle.from_arrays(synthetic.synthetic_bundle(12, first_day=N_DAYS), stats, TICK, device=local)
     ga_rate, ga_colls, _ = ga_rate_of(bun, val, p_total, 5, master)
     ga_rate_tc = {mode: ga_rate_of(bun, val, p_total, 5, master, precision=mode)[0] for mode, _ in TC_MODES}
-    ga_small = None
+    ga_small = ga_small_arl = None
     if world == 1:
         # the reference's own scale (BASELINE configs[0]): population 50, one training day, one validation day
         d1 = synthetic.synthetic_bundle(1, first_day=200)
@@ -441,6 +441,17 @@ def run_ours(args):
         t1 = sgmm_b200.Bundle.from_arrays(d1, st1, TICK, device=local)
         v1 = sgmm_b200.Bundle.from_arrays(synthetic.synthetic_bundle(1, first_day=201), st1, TICK, device=local)
         ga_small = ga_rate_of(t1, v1, 50, 200, master)[0]
+        # the reference's default pipeline co-trains the adversary (pipeline/agent_trainer.py:79: USE_ARL=True)
+        adv0 = (np.random.default_rng(4).standard_normal(1250) * 0.5).astype(np.float32)
+        ga0 = DeviceGA(master, adv0, pop_size=50, sigma=0.05, phi=PHI, fee_rate=FEE, use_arl=True, seed=0, max_generations=420, device=local)
+        ga0.generation(t1, v1); ga0.generation(t1, v1); torch.cuda.synchronize()
+        gr0 = ga0.capture(t1, v1); gr0.replay(); torch.cuda.synchronize()
+        t0_ = time.perf_counter()
+        for _ in range(200):
+            gr0.replay()
+        torch.cuda.synchronize()
+        ga_small_arl = 200 / (time.perf_counter() - t0_)
+        ga0.close()
 
     # ---- BASELINE.json configs[2..4] -------------------------------------------------------------
     configs = {}
@@ -677,6 +688,7 @@ def run_ours(args):
             "ga_workload": f"population {p_total} x {T} bars train + 2880 bars validation"
                            + (" (CUDA-graph replay)" if world == 1 else f" sharded over {world} ranks (eager: evaluate, one NCCL all-gather, select)"),
             "ga_generations_per_sec_config0_pop50_1day": ga_small,
+            "ga_generations_per_sec_config0_pop50_1day_arl": ga_small_arl,
             "tensor_core_h32": tc,
             "configs": configs,
             "checksum": checksum,

@@ -120,7 +120,9 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
                    double* fitness, int32_t* trades, cudaStream_t st);
 // small populations, fast (sgmm_one.cu): policy table for every (bar, inventory) + automaton scan + reference-order sum
 constexpr int64_t SMALL_POP_MAX = 296;      // measured break-even against the sequential kernel: ~300 individuals (profiles/r2_small_population_path.log)
-int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades, cudaStream_t st);
+constexpr int64_t SMALL_POP_MAX_ADV = 148;  // with the adversary (one 512-thread CTA per individual and SM)
+int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, double phi, double fee, double* fitness, int32_t* trades,
+                         cudaStream_t st);
 int launch_trace(const sgmm_bundle* b, const float* mm_genome, int hidden, const float* adv_genome,
                  const int32_t* forced, const int32_t* table, double phi, double fee, const sgmm_trace* tr,
                  double* fitness, int32_t* trades, cudaStream_t st);

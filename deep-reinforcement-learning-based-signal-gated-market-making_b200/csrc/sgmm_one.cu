@@ -21,6 +21,7 @@
 // against the sequential kernel: profiles/r2_small_population_path.log).
 #include "sgmm_internal.h"
 #include "sgmm_rng.cuh"
+#include "sgmm_adversary.cuh"
 #include "sgmm_step_core.h"
 
 namespace sgmm {
@@ -54,7 +55,7 @@ struct PtSmem {
 // order): layer 1 fma chain from b1; layer 2 four chains over k mod 4 from (b2, 0, 0, 0), combined (c0+c2)+(c1+c3); layer 3
 // products summed by the xor-butterfly tree 16, 8, 4, 2, 1 (written out serially: s[l] = s[l] + s[l + m]) plus b3.
 __global__ void __launch_bounds__(PT_THREADS) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const PopArgs mm_in, int64_t pairs_per_task,
-                                                                   float2* __restrict__ code, uint8_t* __restrict__ next)
+                                                                   int raw, float2* __restrict__ code, uint8_t* __restrict__ next)
 {
     __shared__ PtSmem sm;
     const PopArgs mm = resolve(mm_in);
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_table_kernel(const BarSig* 
             }
             const float qa = __fmul_rn(__fadd_rn(pa[0], sm.b3[0]), 5.0f);                  // raw*5.0 (drl_engine.py:39)
             const float qb = __fmul_rn(__fadd_rn(pb[0], sm.b3[1]), 5.0f);
+            if (raw) { codei[p] = make_float2(qa, qb); continue; }                         // adversary: the fills depend on the walk's state
             // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
             const bool fb = (inv2 < 1.0f) && (qb < sg.w);                                  // market_env.py:34,37
             const bool fs = (inv2 > -1.0f) && (qa < sg.z);                                 // :35,:38
@@ -232,12 +234,160 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_THREADS == 1024 ? 1 : 3) wa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// With the adversary (drl_engine.py:42-48) the walk has 20 states (fill_sell_prev, fill_buy_prev, inventory): the policy
+// table holds the raw q = raw*5 of every (bar, inventory) pair, every bar is a map {0..19} -> {0..19} built from it, the
+// bar's integer thresholds and the individual's 20-entry displacement table, and the same prefix scan applies.
+// Maps: 20 entries of 5 bits, six per 32-bit word.
+// ---------------------------------------------------------------------------------------------
+struct Map20 { uint32_t w[4]; };
+__device__ __forceinline__ uint32_t m20_at(const Map20& m, uint32_t e)          // dynamic index
+{
+    const uint32_t hi = e >= 12u, w = hi ? (e >= 18u ? m.w[3] : m.w[2]) : (e >= 6u ? m.w[1] : m.w[0]);
+    const uint32_t base = hi ? (e >= 18u ? 18u : 12u) : (e >= 6u ? 6u : 0u);
+    return (w >> (5u * (e - base))) & 31u;
+}
+template <int S> __device__ __forceinline__ uint32_t m20_get(const Map20& m) { return (m.w[S / 6] >> (5 * (S % 6))) & 31u; }
+template <int S> __device__ __forceinline__ void m20_set(Map20& m, uint32_t v) { m.w[S / 6] |= v << (5 * (S % 6)); }
+template <int S = 0>
+__device__ __forceinline__ void m20_then_rec(const Map20& f, const Map20& g, Map20& out)     // out[s] = g[f[s]]
+{
+    if constexpr (S < 20) { m20_set<S>(out, m20_at(g, m20_get<S>(f))); m20_then_rec<S + 1>(f, g, out); }
+}
+__device__ __forceinline__ Map20 m20_then(const Map20& f, const Map20& g) { Map20 o = {{0u, 0u, 0u, 0u}}; m20_then_rec(f, g, o); return o; }
+template <int S = 0> __device__ __forceinline__ void m20_id_rec(Map20& m) { if constexpr (S < 20) { m20_set<S>(m, (uint32_t)S); m20_id_rec<S + 1>(m); } }
+__device__ __forceinline__ Map20 m20_identity() { Map20 m = {{0u, 0u, 0u, 0u}}; m20_id_rec(m); return m; }
+__device__ __forceinline__ Map20 m20_shfl_up(const Map20& m, int d)
+{
+    Map20 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.w[i] = __shfl_up_sync(0xffffffffu, m.w[i], d);
+    return o;
+}
+
+// one bar's step from state st: displaced offsets, fills against the integer thresholds, next state
+struct AdvStep { int oa, ob; bool fb, fs; uint32_t next; };
+__device__ __forceinline__ AdvStep adv_step(uint32_t st, const float2* __restrict__ code_t, int2 k1, uint32_t at0, uint32_t at1, uint32_t at2)
+{
+    const uint32_t iv = st % 5u;
+    const float2 q = code_t[iv];
+    const uint32_t e = table_lookup(at0, at1, at2, (int)st);
+    AdvStep r;
+    r.oa = max(min(__float2int_rn(q.x), K_CLAMP), -K_CLAMP) + (int)(e & 3u) - 1;          // drl_engine.py:39, market_env.py:26-28
+    r.ob = max(min(__float2int_rn(q.y), K_CLAMP), -K_CLAMP) + (int)(e >> 2) - 1;
+    r.fb = (iv < 4u) && (r.ob < k1.y);                                                     // :34,:37
+    r.fs = (iv > 0u) && (r.oa < k1.x);                                                     // :35,:38
+    r.next = (r.fs ? 10u : 0u) + (r.fb ? 5u : 0u) + iv + (r.fb ? 1u : 0u) - (r.fs ? 1u : 0u);
+    return r;
+}
+template <int S = 0>
+__device__ __forceinline__ void bar_map_rec(Map20& m, const float2* __restrict__ code_t, int2 k1, uint32_t at0, uint32_t at1, uint32_t at2)
+{
+    if constexpr (S < 20) { m20_set<S>(m, adv_step((uint32_t)S, code_t, k1, at0, at1, at2).next); bar_map_rec<S + 1>(m, code_t, k1, at0, at1, at2); }
+}
+
+template <int WALK_THREADS>
+__global__ void __launch_bounds__(WALK_THREADS, 1) walk_account_adv_kernel(const BarSig* __restrict__ sig, const BarPx* __restrict__ px, int64_t T,
+                                                                            const float2* __restrict__ code_all, const PopArgs adv_in, double tick, double phi,
+                                                                            double fee, double* __restrict__ fitness, int32_t* __restrict__ trades)
+{
+    const float2* code = code_all + (int64_t)blockIdx.x * T * 5;          // one CTA per individual
+    __shared__ Map20 s_warp[32];
+    __shared__ uint32_t s_adv[3];
+    __shared__ int s_trades;
+    __shared__ double s_rew[SUM_CHUNK];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_trades = 0;
+    if (tid < 3) s_adv[tid] = 0u;
+    __syncthreads();
+    if (tid < 20) {                                         // the individual's adversary as its displacement table (sgmm_adversary.cuh)
+        const PopArgs advp = resolve(adv_in);
+        const uint32_t e = adversary_entry(make_source(advp, blockIdx.x, (int64_t)1250), tid);
+        atomicOr(&s_adv[tid >> 3], e << ((tid & 7) * 4));
+    }
+    __syncthreads();
+    const uint32_t at0 = s_adv[0], at1 = s_adv[1], at2 = s_adv[2];
+    // ---- 1. every thread composes the maps of its contiguous segment of bars ----
+    const int64_t L = (T + WALK_THREADS - 1) / WALK_THREADS;
+    const int64_t t_lo = (int64_t)tid * L < T ? (int64_t)tid * L : T, t_hi = t_lo + L < T ? t_lo + L : T;
+    Map20 m = m20_identity();
+    for (int64_t t = t_lo; t < t_hi; ++t) {
+        Map20 bm = {{0u, 0u, 0u, 0u}};
+        bar_map_rec(bm, code + t * 5, __ldg(reinterpret_cast<const int2*>(&sig[t].ka1)), at0, at1, at2);
+        m = m20_then(m, bm);
+    }
+    // ---- 2. exclusive scan over the segments ----
+    Map20 inc = m;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const Map20 o = m20_shfl_up(inc, d);
+        if (lane >= d) inc = m20_then(o, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        Map20 w = lane < WALK_THREADS / 32 ? s_warp[lane] : m20_identity();
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            const Map20 o = m20_shfl_up(w, d);
+            if (lane >= d) w = m20_then(o, w);
+        }
+        s_warp[lane] = w;                                   // inclusive over warps
+    }
+    __syncthreads();
+    Map20 before = m20_shfl_up(inc, 1);
+    if (lane == 0) before = m20_identity();
+    if (warp > 0) before = m20_then(s_warp[warp - 1], before);
+    uint32_t st = m20_at(before, 2u);                       // flat, no previous fills (market_env.py:17, drl_engine.py:29)
+    // ---- 3. the fp64 half for the visited states, chunk by chunk; one thread sums each chunk in bar order ----
+    const double pen0 = mul_rn(phi, 0.0), pen1 = mul_rn(phi, 1.0), pen2 = mul_rn(phi, 2.0);       // market_env.py:57
+    int ntr = 0;
+    double total = 0.0;
+    for (int64_t c0 = 0; c0 < T; c0 += SUM_CHUNK) {
+        const int64_t c1 = c0 + SUM_CHUNK < T ? c0 + SUM_CHUNK : T;
+        const int64_t a = t_lo > c0 ? t_lo : c0, b = t_hi < c1 ? t_hi : c1;
+        for (int64_t t = a; t < b; ++t) {
+            const AdvStep r = adv_step(st, code + t * 5, __ldg(reinterpret_cast<const int2*>(&sig[t].ka1)), at0, at1, at2);
+            ntr += (r.fb || r.fs) ? 1 : 0;                                         // drl_engine.py:60-61
+            double pnl = 0.0;                                                      // market_env.py:40
+            if (r.fb || r.fs) {
+                const BarPx p = px[t];
+                const double my_ask = add_rn(p.ask, mul_rn((double)r.oa, tick));   // :30
+                const double my_bid = sub_rn(p.bid, mul_rn((double)r.ob, tick));   // :31
+                double leg_b = sub_rn(p.mid_next, my_bid), leg_s = sub_rn(my_ask, p.mid_next);
+                leg_b = sub_rn(leg_b, mul_rn(my_bid, fee));                        // :46,:48
+                leg_s = sub_rn(leg_s, mul_rn(my_ask, fee));                        // :52,:54
+                pnl = r.fb ? add_rn(pnl, leg_b) : pnl;
+                pnl = r.fs ? add_rn(pnl, leg_s) : pnl;
+            }
+            const int niv = (int)(r.next % 5u);
+            const int ai = niv < 2 ? 2 - niv : niv - 2;
+            s_rew[t - c0] = sub_rn(pnl, ai == 0 ? pen0 : (ai == 1 ? pen1 : pen2));                 // :57-58
+            st = r.next;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int n = (int)(c1 - c0);
+            for (int i = 0; i < n; ++i) total = add_rn(total, s_rew[i]);           // drl_engine.py:54
+        }
+        __syncthreads();
+    }
+    if (ntr) atomicAdd(&s_trades, ntr);
+    __syncthreads();
+    if (tid == 0) {
+        const int n = s_trades;
+        if (n == 0) total = sub_rn(total, 50.0);                                   // drl_engine.py:64-65
+        fitness[blockIdx.x] = total; trades[blockIdx.x] = n;
+    }
+}
+
 }  // namespace one
 
-// Episodes of a small population on `b` (H = 32, exact SGMM-F32 order, no adversary) through the two kernels above.  The
+// Episodes of a small population on `b` (H = 32, exact SGMM-F32 order, with or without the adversary) through the kernels above.  The
 // policy table ([count][T] x 48 B) lives in the bundle's grow-only code buffer (sgmm_account.cu: rollouts sharing it are
 // ordered across streams; the first rollout of a size allocates and must not run under a stream capture).
-int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, double phi, double fee, double* fitness, int32_t* trades, cudaStream_t st)
+int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, double phi, double fee, double* fitness, int32_t* trades,
+                         cudaStream_t st)
 {
     using namespace one;
     const int64_t T = b->T, P = mm.count;
@@ -257,12 +407,13 @@ int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, double phi, do
         if (ppt < ppt_min) ppt = ppt_min;
         const int64_t ntasks = P * ((T * 5 + ppt - 1) / ppt);
         const int64_t blocks = ntasks < want_blocks * 2 ? ntasks : want_blocks * 2;
-        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), PT_THREADS, 0, st>>>(b->sig, T, mm, ppt, code, next);
+        policy_table_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), PT_THREADS, 0, st>>>(b->sig, T, mm, ppt, adv ? 1 : 0, code, next);
         if (int rc = check_cuda(cudaGetLastError(), "policy_table_kernel launch")) return rc;
     }
     int sms2 = 148;
     cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, b->device);
-    if (P <= sms2) walk_account_kernel<1024><<<(unsigned)P, 1024, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
+    if (adv) walk_account_adv_kernel<512><<<(unsigned)P, 512, 0, st>>>(b->sig, b->px, T, code, *adv, b->tick, phi, fee, fitness, trades);
+    else if (P <= sms2) walk_account_kernel<1024><<<(unsigned)P, 1024, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
     else walk_account_kernel<512><<<(unsigned)P, 512, 0, st>>>(b->px, T, code, next, b->tick, phi, fee, fitness, trades);
     if (int rc = check_cuda(cudaGetLastError(), "walk_account_kernel launch")) return rc;
     return release_codes(b, st);

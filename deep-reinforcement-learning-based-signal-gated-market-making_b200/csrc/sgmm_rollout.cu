@@ -507,8 +507,11 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
     // small populations without an adversary: the policy-table path (sgmm_one.cu) unless the caller pinned a geometry
     {
         static const int64_t small_max = [] { const char* e = getenv("SGMM_SMALL_POP_MAX"); return e ? (int64_t)atoll(e) : SMALL_POP_MAX; }();
-        if (!adv && units_per_lane == 0 && warps_per_cta == 0 && mm.count <= small_max)
-            return launch_rollout_small(b, mm, phi, fee, fitness, trades, st);
+        static const int64_t small_max_adv = [] { const char* e = getenv("SGMM_SMALL_POP_MAX_ADV"); return e ? (int64_t)atoll(e) : SMALL_POP_MAX_ADV; }();
+        // (with the adversary the walk kernel runs one CTA per SM: beyond the SM count it only wins on episodes of ~4+ days)
+        const int64_t adv_max = b->T >= 900 ? 2 * small_max_adv : small_max_adv;
+        if (units_per_lane == 0 && warps_per_cta == 0 && mm.count <= (adv ? adv_max : small_max))
+            return launch_rollout_small(b, mm, adv, phi, fee, fitness, trades, st);
     }
     int dev = b->device;
     if (dev >= 0 && dev < 64 && g_sm_count[dev] == 0) {
