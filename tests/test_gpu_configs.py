@@ -432,3 +432,32 @@ def test_cuda_matches_the_committed_long_reference_vectors(sg, orc, name):
     if adv is None:                                                                                  # and the small-population path
         f2, t2 = sg.rollout_population(bun, torch.from_numpy(genomes).cuda(), phi=1e-4, fee_rate=fee)
         assert torch.equal(f2, fit) and torch.equal(t2, trd)
+
+
+@pytest.mark.parametrize("days,T", [(1, 0), (1, 1), (1, 7), (9, 2049), (60, 14400)])
+@pytest.mark.parametrize("use_adv,fee", [(False, 0.0), (True, 0.0), (True, 3e-4)])
+def test_small_population_path_equals_sequential_kernel_and_oracle(sg, orc, days, T, use_adv, fee):
+    """The launcher's two routes for a small population -- policy table + automaton scan (sgmm_one.cu: 5 states, 20 with the
+    adversary) and the sequential kernel (pinned by units_per_lane) -- against each other and the oracle, explicit and seeded."""
+    from sgmm_b200 import synthetic
+    bundle = tuple(a[:T] for a in synthetic.synthetic_bundle(days, first_day=420))
+    stats = synthetic.train_stats_of(synthetic.synthetic_bundle(1, first_day=419))
+    bun = sg.Bundle.from_arrays(bundle, stats, 0.001)
+    P = 7
+    master, genomes = synthetic.policy_like_genomes(P, seed=T + 3, out_scale=4.0, out_bias=(0.1, 0.1))
+    adv = (np.random.default_rng(T + 4).standard_normal((P, 1250)) * 0.6).astype(np.float32) if use_adv else None
+    g = torch.from_numpy(genomes).cuda()
+    a = None if adv is None else torch.from_numpy(adv).cuda()
+    f_small, t_small = sg.rollout_population(bun, g, a, phi=1e-4, fee_rate=fee)
+    f_seq, t_seq = sg.rollout_population(bun, g, a, phi=1e-4, fee_rate=fee, units_per_lane=1)
+    assert torch.equal(f_small, f_seq) and torch.equal(t_small, t_seq)
+    z1, z2 = orc.normalise(bundle, stats)
+    bz = (z1, z2) + bundle[2:]
+    fo, to = orc.rollout_population(bz, 1e-4, 0.001, fee, genomes=genomes, adv_genomes=adv, use_adv=use_adv)
+    assert np.array_equal(bits64(f_small.cpu().numpy()), bits64(fo)) and np.array_equal(t_small.cpu().numpy(), to)
+    # seeded children (and seeded adversaries): both routes regenerate the same genomes
+    am = None if adv is None else torch.from_numpy(adv[0]).cuda()
+    kw = dict(count=9, sigma=0.05, seed=21, generation=2, first_index=5, adv_master=am, phi=1e-4, fee_rate=fee)
+    fs1, ts1 = sg.rollout_seeded(bun, torch.from_numpy(master).cuda(), **kw)
+    fs2, ts2 = sg.rollout_seeded(bun, torch.from_numpy(master).cuda(), units_per_lane=4, **kw)
+    assert torch.equal(fs1, fs2) and torch.equal(ts1, ts2)
