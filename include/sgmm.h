@@ -137,9 +137,12 @@ typedef struct {
  *   - rollouts on one bundle must be ordered (one stream, or serialised): they share the scratch;
  *   - the first rollout of a given size allocates and therefore must not run under a stream capture (run one eagerly,
  *     then capture; a buffer that has been handed out is never freed before sgmm_bundle_destroy).
- * H = 32 rollouts are one kernel with no per-rollout scratch.  The tensor-core precisions read a per-(bundle, fee_rate)
- * table of the reference's exact fp64 P&L legs (272 B per bar), built on the first rollout with that fee rate: that
- * first rollout must not run under a stream capture either. */
+ * H = 32 rollouts of more than ~300 individuals are one kernel with no per-rollout scratch.  SMALL populations (up to 296
+ * individuals, 148 with an adversary; exact precision, default launch geometry) take the policy-table path instead (the
+ * exact policy for every (bar, inventory) in parallel + a prefix scan over the inventory automaton, bit-identical results):
+ * its table ([count][T] x 48 B) lives in the same grow-only code buffer of the bundle, so the same two rules apply to them.
+ * The tensor-core precisions with an adversary read a per-(bundle, fee_rate) table of the reference's exact fp64 P&L legs
+ * (144 B per bar), built on the first such rollout: that first rollout must not run under a stream capture either. */
 int sgmm_rollout_population(const sgmm_bundle* bundle, const sgmm_population* mm,
                             const sgmm_population* adv, const sgmm_rollout_params* params,
                             double* fitness, int32_t* trades, void* stream);
