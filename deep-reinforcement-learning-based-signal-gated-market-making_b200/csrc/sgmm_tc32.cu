@@ -32,7 +32,9 @@
 // walker's 25 dependent fp64 adds per chunk -- the one piece of fp64 that cannot leave the kernel without 8 B of HBM traffic
 // per env-step -- starve behind it (an fp64 instruction waits for a gap in tcgen05.mma activity, profiles/r1_fp64_under_mma.txt);
 // with NO fp64 at all the kernel runs at 2.30 ms (profiles/r2_tc32_dbg1.log, dbg=1), i.e. fp64 costs 5 %, not the factor
-// the shared-pipe counter suggests.  The
+// the shared-pipe counter suggests.  For the adversary a fifth design -- rewards of all four (fill_sell_prev, fill_buy_prev)
+// combinations in E3 from a shared-memory leg ring, groups of 8 individuals with the tables in the unused operand space --
+// ran at 8.5 ms at config 3's 2048 pairs against 3.25 ms for the marks scheme (profiles/r2_tc32_adv_tables_in_e3.log).  The
 // adversary path is correct (tests/test_gpu_tc32.py) but not faster than the exact kernel (6.3 vs 5.3 ms): without its
 // accounting it still takes 4.9 ms, with one combination instead of four 4.3 ms (profiles/r2_tc32_dbg2.log) -- the extra
 // walker -> E3 -> walker round trip per chunk stalls the D3 drain, i.e. the MMA pipeline.
