@@ -8,7 +8,7 @@ source files the path lives in (plus its caller) from where they lie under /root
     Env/market_env.py      FTPEnv.step / reset                      
     Env/drl_engine.py      evaluate_individual, DRLEngine            (a3-a5, a8, a11)
     models/model.py        TradingPolicy, AdversaryPolicy, NeuroEvolution (a4, a6, a7, a9, a10)
-    pipeline/agent_trainer.py   the caller of the path (8b), for the drop-in proof
+    pipeline/agent_trainer.py, pipeline/evaluator.py   the callers of the path (8b), for the drop-in proof
 
 into oracle/_ref/ together with MANIFEST.json (sha256 of every file, so a test can prove they are unmodified).  Nothing
 under oracle/_ref/ is ever committed (the reference's sources must not enter this repository's history) and the PRODUCT
@@ -26,7 +26,7 @@ DST = os.path.join(ROOT, "oracle", "_ref")
 FILES = ("Env/market_env.py", "Env/drl_engine.py", "models/model.py",
          # the path's CALLER, staged for the drop-in proof only (tests/test_gpu_dropin_pipeline.py runs it unchanged with
          # this repository's dropin/ shadowing Env.* and models.model); never imported by oracle/run_ref.py
-         "pipeline/agent_trainer.py")
+         "pipeline/agent_trainer.py", "pipeline/evaluator.py")
 
 
 def _sha(path):

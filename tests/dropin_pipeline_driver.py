@@ -84,6 +84,8 @@ class BacktestVisualizer:
         plotted["rows"], plotted["metrics"] = len(df), {k: float(v) for k, v in metrics.items()}
 
 
+import torch                # noqa: E402
+torch.manual_seed(20241018)  # the engine draws its Philox key and the initial policies from torch's global generator: make the run repeatable
 import sgmm_b200            # noqa: E402  (the analytics class of this repository mirrors analytics/mm_analyzer.py)
 fake_module("models.GateUnits", SGU1=SGU1, SGU2=SGU2)
 fake_module("loaders")
@@ -113,6 +115,25 @@ import Env.drl_engine, Env.market_env, Env.recorder, models.model      # noqa: E
 
 at.run_agent_training_pipeline(SYMBOL, (20240401, 20240528), PHI=PHI, TICK_SIZE=0.001, USE_FEE=False, USE_ARL=True)
 
+# ---- the other caller: pipeline/evaluator.py::run_drl_backtest (the per-bar backtest loop with record_detailed + parquet) on a
+# synthetic two-day bundle with the agent just trained; then the SAME backtest as one device launch (rollout_trace)
+import pipeline.evaluator as ev             # noqa: E402  the reference's module, unmodified (oracle/_ref)
+from sgmm_b200 import synthetic             # noqa: E402
+bt_bundle = synthetic.synthetic_bundle(2, first_day=900)
+bt_stats = synthetic.train_stats_of(bt_bundle)
+weight_path = f"checkpoints/{SYMBOL}/with_adv/agent_best_val_{PHI}.pth"
+ev.run_drl_backtest(SYMBOL, "arl", weight_path, bt_bundle, PHI, 0.0003, bt_stats)
+bt_parquet = f"output/{SYMBOL}/arl/backtest_{PHI}.parquet"
+pol = sgmm_b200.TradingPolicy(); pol.load_state_dict(torch.load(weight_path, weights_only=True))
+bun = sgmm_b200.Bundle.from_arrays(bt_bundle, bt_stats, 0.001)
+fit, trades, tr = sgmm_b200.rollout_trace(bun, pol.get_weights().numpy(), phi=PHI, fee_rate=0.0003)
+dev_df = sgmm_b200.StrategyRecorder.from_trace(tr, bt_bundle).to_dataframe()
+ref_df = pd.read_parquet(bt_parquet)
+same_cols = {}
+for c in ("off_a", "off_b", "fill_buy", "fill_sell", "inventory", "cash", "reward", "pnl_reward", "inventory_reward", "fee_paid",
+          "spread", "wealth", "cum_reward", "skew", "cum_fees", "realized_pnl", "unrealized_pnl"):
+    same_cols[c] = bool(np.array_equal(np.asarray(dev_df[c]), np.asarray(ref_df[c])))
+
 csv = f"output/{SYMBOL}/phi_{PHI}_S3_TEST_results.csv"
 ck = f"checkpoints/{SYMBOL}/with_adv/agent_best_val_{PHI}.pth"
 print(json.dumps({
@@ -122,4 +143,6 @@ print(json.dumps({
     "env_class": f"{at.FTPEnv.__module__}.{at.FTPEnv.__name__}",
     "csv": os.path.abspath(csv), "csv_exists": os.path.exists(csv), "checkpoint": os.path.abspath(ck),
     "checkpoint_exists": os.path.exists(ck), "plotted": plotted, "days_loaded": state["day"] + 1,
+    "evaluator": ev.__file__, "backtest_parquet": os.path.abspath(bt_parquet), "backtest_rows": int(len(ref_df)),
+    "backtest_device_trace_matches": same_cols, "backtest_fitness": float(fit), "backtest_cum_reward": float(ref_df["cum_reward"].iloc[-1]),
 }))

@@ -5,7 +5,8 @@ The caller is the reference's own file, staged byte for byte under oracle/_ref (
 the GPU box).  SGU models, loaders, parquet data and the plot are faked (tests/dropin_pipeline_driver.py), as in
 oracle/make_golden_prep.py.  The run covers: load_signals_bundle x3, train_stats, DRLEngine(pop 50, use_arl).train for the
 reference's hard-coded 100 generations, checkpoint save + reload, the per-bar blind-test loop over FTPEnv.step /
-TradingPolicy.forward / StrategyRecorder.record, to_dataframe, StrategyAnalytics.
+TradingPolicy.forward / StrategyRecorder.record, to_dataframe, StrategyAnalytics; then pipeline/evaluator.py::run_drl_backtest
+(record_detailed + parquet) against the same backtest done as one device launch.
 """
 import json
 import os
@@ -48,5 +49,12 @@ def test_reference_agent_training_pipeline_runs_unchanged_on_the_b200_backend(tm
     assert len(df) == n_test == info["plotted"]["rows"]
     assert df["inventory"].abs().max() <= 2
     assert info["plotted"]["metrics"]["Trades"] == int(df["is_trade"].sum())
+    # pipeline/evaluator.py::run_drl_backtest (unmodified) ran its per-bar loop on FTPEnv / TradingPolicy / StrategyRecorder.
+    # record_detailed and wrote its parquet; the same backtest as ONE device launch (rollout_trace + StrategyRecorder.from_trace)
+    # gives the same frame column for column, bit for bit (offsets, fills, inventory, cash, rewards, fees, derived columns)
+    assert info["evaluator"].endswith(os.path.join("oracle", "_ref", "pipeline", "evaluator.py"))
+    assert info["backtest_rows"] == 480 and os.path.exists(info["backtest_parquet"])
+    assert all(info["backtest_device_trace_matches"].values()), info["backtest_device_trace_matches"]
+    assert info["backtest_fitness"] == info["backtest_cum_reward"]
     sd = torch.load(info["checkpoint"], weights_only=True)
     assert list(sd.keys()) == [f"net.{i}.{p}" for i in (0, 2, 4) for p in ("weight", "bias")]
