@@ -119,7 +119,7 @@ int launch_rollout(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, 
                    double phi, double fee, int units_per_lane, int warps_per_cta,
                    double* fitness, int32_t* trades, cudaStream_t st);
 // small populations, fast (sgmm_one.cu): policy table for every (bar, inventory) + automaton scan + reference-order sum
-constexpr int64_t SMALL_POP_MAX = 296;      // measured break-even against the sequential kernel: ~300 individuals (profiles/r2_small_population_path.log)
+constexpr int64_t SMALL_POP_MAX = 400;      // measured break-even against the sequential kernel: ~420 individuals (profiles/r2_small_population_path.log)
 constexpr int64_t SMALL_POP_MAX_ADV = 148;  // with the adversary (one 512-thread CTA per individual and SM)
 int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, const PopArgs* adv, double phi, double fee, double* fitness, int32_t* trades,
                          cudaStream_t st);

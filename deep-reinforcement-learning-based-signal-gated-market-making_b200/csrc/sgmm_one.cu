@@ -49,9 +49,10 @@ struct PtSmem {
     float b3[2];
 };
 
-// One (bar, inventory) pair per THREAD, the individual's weights broadcast from shared memory: ~1 700 instructions per pair
-// and thread, i.e. ~53 warp instructions per pair instead of the ~110 (42 of them shuffles) of the lane-per-hidden-unit
-// mapping, FMA-pipe bound instead of shuffle bound.  Same operations in the same order as trace_kernel_h32 (SGMM-F32
+// (Bar, inventory) pairs per THREAD -- two at a time, so that every broadcast weight load feeds two fma chains -- with the
+// individual's weights broadcast from shared memory: ~53 warp instructions per pair instead of the ~110 (42 of them
+// shuffles) of a lane-per-hidden-unit mapping, FMA-pipe / shared-load bound instead of shuffle bound (measured: lane per
+// hidden unit 2.5x slower, one pair per thread 1.15x slower than this).  Same operations in the same order as trace_kernel_h32 (SGMM-F32
 // order): layer 1 fma chain from b1; layer 2 four chains over k mod 4 from (b2, 0, 0, 0), combined (c0+c2)+(c1+c3); layer 3
 // products summed by the xor-butterfly tree 16, 8, 4, 2, 1 (written out serially: s[l] = s[l] + s[l + m]) plus b3.
 __global__ void __launch_bounds__(PT_THREADS) policy_table_kernel(const BarSig* __restrict__ sig, int64_t T, const PopArgs mm_in, int64_t pairs_per_task,
@@ -87,51 +88,73 @@ __global__ void __launch_bounds__(PT_THREADS) policy_table_kernel(const BarSig* 
         const int64_t p_lo = (task - ind * tasks_per_ind) * pairs_per_task, p_hi = p_lo + pairs_per_task < pairs ? p_lo + pairs_per_task : pairs;
         float2* codei = code + ind * pairs;
         uint8_t* nexti = next + ind * T * 8;
-        for (int64_t p = p_lo + threadIdx.x; p < p_hi; p += PT_THREADS) {
-            const int64_t t = p / 5;
-            const int iv = (int)(p - t * 5);
-            const float4 sg = __ldg(reinterpret_cast<const float4*>(&sig[t]));          // z1, z2, tha, thb
-            const float inv2 = (float)(iv - 2) * 0.5f;                                     // drl_engine.py:35
+        // TWO pairs per thread and round (p and p + PT_THREADS): every broadcast weight load feeds two fma chains
+        for (int64_t p0 = p_lo + threadIdx.x; p0 < p_hi; p0 += 2 * PT_THREADS) {
+            const int64_t pp[2] = {p0, p0 + PT_THREADS};
+            const bool ok1 = pp[1] < p_hi;
+            float4 sg[2]; float inv2[2]; int ivv[2]; int64_t tt[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int64_t p = (r == 0 || ok1) ? pp[r] : pp[0];
+                tt[r] = p / 5; ivv[r] = (int)(p - tt[r] * 5);
+                sg[r] = __ldg(reinterpret_cast<const float4*>(&sig[tt[r]]));                // z1, z2, tha, thb
+                inv2[r] = (float)(ivv[r] - 2) * 0.5f;                                       // drl_engine.py:35
+            }
             // ---- TradingPolicy.forward in SGMM-F32 order (models/model.py:9-15) ----
-            float h1[H];
+            float h1[2][H];
 #pragma unroll
             for (int j = 0; j < H; ++j) {
                 const float4 w = sm.l1[j];
-                float v = __fmaf_rn(w.x, sg.x, w.w);
-                v = __fmaf_rn(w.y, sg.y, v);
-                v = __fmaf_rn(w.z, inv2, v);
-                h1[j] = fmaxf(v, 0.0f);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    float v = __fmaf_rn(w.x, sg[r].x, w.w);
+                    v = __fmaf_rn(w.y, sg[r].y, v);
+                    v = __fmaf_rn(w.z, inv2[r], v);
+                    h1[r][j] = fmaxf(v, 0.0f);
+                }
             }
-            float pa[H], pb[H];
+            float pa[2][H], pb[2][H];
 #pragma unroll
             for (int j = 0; j < H; ++j) {
-                float c0 = sm.b2[j], c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+                float c0[2] = {sm.b2[j], sm.b2[j]}, c1[2] = {0.0f, 0.0f}, c2[2] = {0.0f, 0.0f}, c3[2] = {0.0f, 0.0f};
 #pragma unroll
                 for (int k = 0; k < H; k += 4) {
                     const float4 w = *reinterpret_cast<const float4*>(&sm.w2[j][k]);
-                    c0 = __fmaf_rn(w.x, h1[k + 0], c0);
-                    c1 = __fmaf_rn(w.y, h1[k + 1], c1);
-                    c2 = __fmaf_rn(w.z, h1[k + 2], c2);
-                    c3 = __fmaf_rn(w.w, h1[k + 3], c3);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        c0[r] = __fmaf_rn(w.x, h1[r][k + 0], c0[r]);
+                        c1[r] = __fmaf_rn(w.y, h1[r][k + 1], c1[r]);
+                        c2[r] = __fmaf_rn(w.z, h1[r][k + 2], c2[r]);
+                        c3[r] = __fmaf_rn(w.w, h1[r][k + 3], c3[r]);
+                    }
                 }
-                const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)), 0.0f);
                 const float2 w3 = sm.w3[j];
-                pa[j] = __fmul_rn(w3.x, h2);
-                pb[j] = __fmul_rn(w3.y, h2);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float h2 = fmaxf(__fadd_rn(__fadd_rn(c0[r], c2[r]), __fadd_rn(c1[r], c3[r])), 0.0f);
+                    pa[r][j] = __fmul_rn(w3.x, h2);
+                    pb[r][j] = __fmul_rn(w3.y, h2);
+                }
             }
 #pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
+            for (int r = 0; r < 2; ++r) {
 #pragma unroll
-                for (int l = 0; l < m; ++l) { pa[l] = __fadd_rn(pa[l], pa[l + m]); pb[l] = __fadd_rn(pb[l], pb[l + m]); }
+                for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+                    for (int l = 0; l < m; ++l) { pa[r][l] = __fadd_rn(pa[r][l], pa[r][l + m]); pb[r][l] = __fadd_rn(pb[r][l], pb[r][l + m]); }
+                }
+                if (r == 1 && !ok1) break;
+                const int64_t p = pp[r], t = tt[r];
+                const int iv = ivv[r];
+                const float qa = __fmul_rn(__fadd_rn(pa[r][0], sm.b3[0]), 5.0f);              // raw*5.0 (drl_engine.py:39)
+                const float qb = __fmul_rn(__fadd_rn(pb[r][0], sm.b3[1]), 5.0f);
+                if (raw) { codei[p] = make_float2(qa, qb); continue; }                        // adversary: the fills depend on the walk's state
+                // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
+                const bool fb = (inv2[r] < 1.0f) && (qb < sg[r].w);                           // market_env.py:34,37
+                const bool fs = (inv2[r] > -1.0f) && (qa < sg[r].z);                          // :35,:38
+                codei[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
+                nexti[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));              // :45,:51
             }
-            const float qa = __fmul_rn(__fadd_rn(pa[0], sm.b3[0]), 5.0f);                  // raw*5.0 (drl_engine.py:39)
-            const float qb = __fmul_rn(__fadd_rn(pb[0], sm.b3[1]), 5.0f);
-            if (raw) { codei[p] = make_float2(qa, qb); continue; }                         // adversary: the fills depend on the walk's state
-            // ---- integer half of the env step: rounding folded into the per-bar float thresholds, as rollout_kernel_h32 ----
-            const bool fb = (inv2 < 1.0f) && (qb < sg.w);                                  // market_env.py:34,37
-            const bool fs = (inv2 > -1.0f) && (qa < sg.z);                                 // :35,:38
-            codei[p] = make_float2(fs ? qa : __int_as_float(SGMM_CODE_NOFILL_F), fb ? qb : __int_as_float(SGMM_CODE_NOFILL_F));
-            nexti[t * 8 + iv] = (uint8_t)(iv + (fb ? 1 : 0) - (fs ? 1 : 0));               // :45,:51
         }
     }
 }
@@ -402,8 +425,8 @@ int launch_rollout_small(const sgmm_bundle* b, const PopArgs& mm, const PopArgs*
         // task = (individual, range of pairs): ranges of whole 128-pair rounds, sized so that the GPU gets ~8 blocks per SM
         const int64_t want_blocks = (int64_t)sms * 8;
         int64_t ppt = (P * T * 5 + want_blocks - 1) / want_blocks;
-        ppt = (ppt + PT_THREADS - 1) / PT_THREADS * PT_THREADS;
-        const int64_t ppt_min = mm.genomes ? PT_THREADS : 4 * PT_THREADS;      // seeded children: staging costs ~10 Philox calls per thread
+        ppt = (ppt + 2 * PT_THREADS - 1) / (2 * PT_THREADS) * (2 * PT_THREADS);
+        const int64_t ppt_min = mm.genomes ? 2 * PT_THREADS : 4 * PT_THREADS;      // seeded children: staging costs ~10 Philox calls per thread
         if (ppt < ppt_min) ppt = ppt_min;
         const int64_t ntasks = P * ((T * 5 + ppt - 1) / ppt);
         const int64_t blocks = ntasks < want_blocks * 2 ? ntasks : want_blocks * 2;

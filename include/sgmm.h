@@ -137,7 +137,7 @@ typedef struct {
  *   - rollouts on one bundle must be ordered (one stream, or serialised): they share the scratch;
  *   - the first rollout of a given size allocates and therefore must not run under a stream capture (run one eagerly,
  *     then capture; a buffer that has been handed out is never freed before sgmm_bundle_destroy).
- * H = 32 rollouts of more than ~300 individuals are one kernel with no per-rollout scratch.  SMALL populations (up to 296
+ * H = 32 rollouts of more than 400 individuals are one kernel with no per-rollout scratch.  SMALL populations (up to 400
  * individuals, 148 with an adversary; exact precision, default launch geometry) take the policy-table path instead (the
  * exact policy for every (bar, inventory) in parallel + a prefix scan over the inventory automaton, bit-identical results):
  * its table ([count][T] x 48 B) lives in the same grow-only code buffer of the bundle, so the same two rules apply to them.
